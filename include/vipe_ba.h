@@ -1,0 +1,114 @@
+/*
+ * vipe_ba.h -- C ABI of the B200-native dense bundle adjustment (libvipe_ba.so).
+ *
+ * This is the drop-in boundary for ONE reference operator:
+ *
+ *     slam_ext.ba(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj,
+ *                 t0, t1, iterations, lm, ep, motion_only) -> [dx, dz]
+ *
+ * bound in the reference at csrc/slam_ext/slam.cpp:24-27,32 (pybind) and implemented by
+ * `ba_cuda`, csrc/slam_ext/geom_kernels.cu:1283-1404.  The entry points below are what a binding for
+ * that operator calls; vipe_b200/ext/slam_ext.py is such a binding (ctypes + torch tensors) and
+ * INTEGRATION.md shows the one a ViPE maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch types.  Device pointers are marked DEV, host pointers HOST.
+ *  - all floating point device arrays are fp32, contiguous, in the reference's layouts
+ *    (geom_kernels.cu:1287-1299): poses[N,7]=(tx,ty,tz,qx,qy,qz,qw), disps[N,ht,wd], intrinsics[4],
+ *    disps_sens[N,ht,wd], targets/weights[E,2,ht,wd], eta[K,ht,wd].
+ *  - poses and disps are updated IN PLACE (geom_kernels.cu:1353,1393,1397); everything else is read-only.
+ *  - every function returns 0 on success, non-zero on error; vipe_ba_last_error() describes the last
+ *    failure on the calling thread.  A failed Cholesky factorisation is NOT an error: like the reference
+ *    (geom_kernels.cu:1181-1188) it yields dx = 0 for that iteration.
+ *  - nothing in this library synchronises the stream or allocates device memory: the caller supplies one
+ *    workspace (size from vipe_ba_workspace_bytes) and a cudaStream_t (passed as void*).
+ */
+#ifndef VIPE_BA_H_
+#define VIPE_BA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vipe_ba_plan vipe_ba_plan;
+
+/* ABI version of this header (bumped on any signature change). */
+int vipe_ba_abi_version(void);
+const char *vipe_ba_last_error(void);
+
+/*
+ * Index bookkeeping of one BA problem; replaces geom_kernels.cu:1301-1308 (ts / ii_exp / jj_exp / _unique),
+ * the four per-iteration host CSR builds of accum_cuda (:946-981) and the triple list of schur_block
+ * (:1209-1240).  Depends only on (ii, jj, N, ht, wd, t0, t1), so it is built once per call (or cached by
+ * the caller across calls on the same graph).
+ *
+ * ii, jj: HOST int64[n_edges].  rank/world: keyframe sharding; rank 0 of 1 = whole problem.
+ */
+int vipe_ba_plan_create(const int64_t *ii, const int64_t *jj, int64_t n_edges, int64_t n_frames, int ht, int wd,
+                        int t0, int t1, int rank, int world, vipe_ba_plan **out);
+void vipe_ba_plan_destroy(vipe_ba_plan *plan);
+
+/* K = |kx|, kx = sorted unique of cat(arange(t0,t1), ii)  (geom_kernels.cu:1305-1308). */
+int64_t vipe_ba_plan_num_kx(const vipe_ba_plan *plan);
+/* HOST int64[K] <- kx;  HOST int64[(t1-t0)+E] <- kk_exp (inverse indices of the unique). */
+int vipe_ba_plan_copy_kx(const vipe_ba_plan *plan, int64_t *kx_out);
+int vipe_ba_plan_copy_kk_exp(const vipe_ba_plan *plan, int64_t *kk_out);
+/* Per-source-frame CSR (the ptrs/idxs of accum_cuda(.., ii, kx)): HOST int64[K+1], HOST int64[E]. */
+int vipe_ba_plan_copy_csr(const vipe_ba_plan *plan, int64_t *ptrs_out, int64_t *idxs_out);
+/* Owned kx positions [lo, hi) of this rank, and of any rank. */
+int vipe_ba_plan_owned_range(const vipe_ba_plan *plan, int rank, int64_t *lo, int64_t *hi);
+/* Number of (pose_a, pose_b, frame) triples schur_block would enumerate (:1225-1240); bookkeeping check. */
+int64_t vipe_ba_plan_num_schur_triples(const vipe_ba_plan *plan);
+/* Largest number of edges leaving one owned source frame. */
+int vipe_ba_plan_max_degree(const vipe_ba_plan *plan);
+
+/* Bytes of DEVICE workspace one run needs (index tables + per-tile partials + reduced camera system). */
+size_t vipe_ba_workspace_bytes(const vipe_ba_plan *plan);
+/* Copy the plan's index tables into the head of the workspace (async on `stream`). Call once per workspace. */
+int vipe_ba_plan_upload(const vipe_ba_plan *plan, void *workspace /*DEV*/, void *stream);
+
+typedef struct vipe_ba_tensors {
+    float *poses;             /* DEV [N,7]      in/out */
+    float *disps;             /* DEV [N,ht,wd]  in/out */
+    const float *intrinsics;  /* DEV [4] */
+    const float *disps_sens;  /* DEV [N,ht,wd] */
+    const float *targets;     /* DEV [E,2,ht,wd] */
+    const float *weights;     /* DEV [E,2,ht,wd] */
+    const float *eta;         /* DEV [K,ht,wd]; may be NULL when motion_only */
+    float *dx_out;            /* DEV [t1-t0,6]  update of the last iteration */
+    float *dz_out;            /* DEV [K,ht*wd]  update of the last iteration; may be NULL when motion_only */
+} vipe_ba_tensors;
+
+/*
+ * The whole operator: `iterations` Gauss-Newton steps, no host synchronisation, all work on `stream`.
+ * Single-rank plans only (world == 1).  Replaces ba_cuda, geom_kernels.cu:1283-1404.
+ */
+int vipe_ba_run(const vipe_ba_plan *plan, const vipe_ba_tensors *t, void *workspace, int iterations, float lm,
+                float ep, int motion_only, void *stream);
+
+/*
+ * The same iteration split at its one exchange point, for keyframe-sharded multi-GPU runs:
+ *   vipe_ba_linearize   : stages 1-3 on this rank's source frames -> partial reduced camera system
+ *   (caller all-reduces the buffer returned by vipe_ba_system_buffer over NCCL)
+ *   vipe_ba_solve_update: damped Cholesky solve (replicated), back-substitution + retraction of owned frames.
+ */
+int vipe_ba_linearize(const vipe_ba_plan *plan, const vipe_ba_tensors *t, void *workspace, int motion_only,
+                      void *stream);
+int vipe_ba_solve_update(const vipe_ba_plan *plan, const vipe_ba_tensors *t, void *workspace, float lm, float ep,
+                         int motion_only, void *stream);
+/* DEV fp64 buffer holding [H (n x n, row-major, lower triangle valid) ; b (n)], n = 6*(t1-t0). */
+void *vipe_ba_system_buffer(const vipe_ba_plan *plan, void *workspace, int64_t *n_out, int64_t *count_out);
+
+/* Test hooks: DEV fp32 [K,HW] buffers written by the last linearize (Q = 1/C and Q*w of geom_kernels.cu:1365-1370). */
+float *vipe_ba_debug_q(const vipe_ba_plan *plan, void *workspace);
+float *vipe_ba_debug_qw(const vipe_ba_plan *plan, void *workspace);
+/* Number of kernels the last vipe_ba_run / linearize+solve_update pair enqueued (for bench.py's gpu_launches). */
+int64_t vipe_ba_launch_count(const vipe_ba_plan *plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIPE_BA_H_ */

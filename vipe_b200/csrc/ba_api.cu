@@ -1,0 +1,362 @@
+// C ABI of libvipe_ba.so (include/vipe_ba.h): plan construction (index bookkeeping on the host, once per
+// graph), workspace layout, and the stream-ordered Gauss-Newton loop.  No torch, no allocation, no sync.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/vipe_ba.h"
+#include "ba_launch.h"
+
+using namespace vba;
+
+static thread_local std::string g_err;
+static int fail(const std::string &msg) {
+    g_err = msg;
+    return 1;
+}
+#define VBA_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct vipe_ba_plan {
+    int64_t E = 0, N = 0;
+    int ht = 0, wd = 0, HW = 0, t0 = 0, t1 = 0, P = 0, K = 0;
+    int rank = 0, world = 1;
+    int n = 0, npad = 0;
+    int NT = 256, PPT = 1, ntile = 0;
+    int NTm = 256, PPTm = 1, ntile_m = 0;  // motion-only tile shape (no staging buffer => always the widest)
+    int k_lo = 0, k_hi = 0, dmax = 0;
+    int64_t n_triples = 0;
+    std::vector<int64_t> kx, kk_exp;
+    std::vector<int> kx32, fptr, fedge, e_jj;
+    std::vector<long long> gbase, mbase;
+    std::vector<int64_t> own_lo, own_hi;
+    // workspace layout (byte offsets)
+    size_t off_kx = 0, off_fptr = 0, off_fedge = 0, off_ejj = 0, off_gbase = 0, off_mbase = 0, idx_bytes = 0;
+    size_t off_epart = 0, off_gpart = 0, off_msc = 0, off_q = 0, off_qw = 0, off_sys = 0, off_dx = 0, off_flag = 0;
+    size_t total = 0;
+    std::vector<unsigned char> blob;  // host image of the index tables
+    mutable int64_t launches = 0;
+};
+
+extern "C" int vipe_ba_abi_version(void) { return 1; }
+extern "C" const char *vipe_ba_last_error(void) { return g_err.c_str(); }
+
+extern "C" int vipe_ba_plan_create(const int64_t *ii, const int64_t *jj, int64_t n_edges, int64_t n_frames, int ht,
+                                   int wd, int t0, int t1, int rank, int world, vipe_ba_plan **out) {
+    if (!out) return fail("out is null");
+    *out = nullptr;
+    if (n_edges < 0 || n_frames <= 0 || ht <= 0 || wd <= 0) return fail("bad sizes");
+    if (t0 < 0 || t1 < t0 || t1 > n_frames) return fail("need 0 <= t0 <= t1 <= n_frames");
+    if (world < 1 || rank < 0 || rank >= world) return fail("bad rank/world");
+    if (n_edges > 0 && (!ii || !jj)) return fail("ii/jj null");
+    for (int64_t e = 0; e < n_edges; e++) {
+        if (ii[e] < 0 || ii[e] >= n_frames || jj[e] < 0 || jj[e] >= n_frames)
+            return fail("edge " + std::to_string(e) + " references a frame outside [0, n_frames)");
+    }
+    auto *p = new vipe_ba_plan();
+    p->E = n_edges;
+    p->N = n_frames;
+    p->ht = ht;
+    p->wd = wd;
+    p->HW = ht * wd;
+    p->t0 = t0;
+    p->t1 = t1;
+    p->P = t1 - t0;
+    p->rank = rank;
+    p->world = world;
+    p->n = 6 * p->P;
+    p->npad = std::max(kCholBlock, (p->n + kCholBlock - 1) / kCholBlock * kCholBlock);
+    const int P = p->P;
+    const int64_t E = n_edges;
+
+    // kx = sorted unique of cat(arange(t0,t1), ii);  kk_exp = inverse   (geom_kernels.cu:1301-1308)
+    std::vector<char> present(n_frames, 0);
+    for (int t = t0; t < t1; t++) present[t] = 1;
+    for (int64_t e = 0; e < E; e++) present[ii[e]] = 1;
+    std::vector<int> slot(n_frames, -1);
+    for (int64_t f = 0; f < n_frames; f++)
+        if (present[f]) {
+            slot[f] = (int)p->kx.size();
+            p->kx.push_back(f);
+        }
+    p->K = (int)p->kx.size();
+    p->kk_exp.resize(P + E);
+    for (int t = 0; t < P; t++) p->kk_exp[t] = slot[t0 + t];
+    for (int64_t e = 0; e < E; e++) p->kk_exp[P + e] = slot[ii[e]];
+
+    // CSR of edges by source frame, ascending edge id inside a frame (accum_cuda's ptrs/idxs, :946-981)
+    const int K = p->K;
+    p->fptr.assign(K + 1, 0);
+    for (int64_t e = 0; e < E; e++) p->fptr[slot[ii[e]] + 1]++;
+    for (int k = 0; k < K; k++) p->fptr[k + 1] += p->fptr[k];
+    p->fedge.resize(E);
+    {
+        std::vector<int> cur(p->fptr.begin(), p->fptr.end() - 1);
+        for (int64_t e = 0; e < E; e++) p->fedge[cur[slot[ii[e]]]++] = (int)e;
+    }
+    p->e_jj.resize(E);
+    for (int64_t e = 0; e < E; e++) p->e_jj[e] = (int)jj[e];
+    p->kx32.resize(K);
+    for (int k = 0; k < K; k++) p->kx32[k] = (int)p->kx[k];
+
+    // number of schur_block triples (:1209-1240): per frame k, (rows whose target pose is in the window)^2
+    for (int k = 0; k < K; k++) {
+        int64_t rows = 0;
+        const int f = (int)p->kx[k];
+        if (f >= t0 && f < t1) rows++;  // the Ei row of pose f
+        for (int s = p->fptr[k]; s < p->fptr[k + 1]; s++) {
+            const int j = p->e_jj[p->fedge[s]];
+            if (j >= t0 && j < t1) rows++;
+        }
+        p->n_triples += rows * rows;
+    }
+
+    // keyframe sharding: contiguous kx ranges balanced by (out-degree + 1)
+    p->own_lo.assign(world, 0);
+    p->own_hi.assign(world, 0);
+    {
+        std::vector<int64_t> cost(K + 1, 0);
+        for (int k = 0; k < K; k++) cost[k + 1] = cost[k] + (p->fptr[k + 1] - p->fptr[k]) + 1;
+        int k = 0;
+        for (int r = 0; r < world; r++) {
+            p->own_lo[r] = k;
+            const int64_t target = cost[K] * (r + 1) / world;
+            while (k < K && cost[k + 1] <= target) k++;
+            if (r == world - 1) k = K;
+            p->own_hi[r] = k;
+        }
+    }
+    p->k_lo = (int)p->own_lo[rank];
+    p->k_hi = (int)p->own_hi[rank];
+    p->dmax = 0;
+    for (int k = p->k_lo; k < p->k_hi; k++) p->dmax = std::max(p->dmax, p->fptr[k + 1] - p->fptr[k]);
+
+    if (!tile_config(p->HW, std::max(p->dmax, 1), false, p->NT, p->PPT)) {
+        delete p;
+        return fail("a source frame has too many outgoing edges for the shared-memory staging buffer");
+    }
+    p->ntile = (p->HW + p->NT * p->PPT - 1) / (p->NT * p->PPT);
+    // motion-only shares the partial layout (ntile), so it uses the same tile shape
+    p->NTm = p->NT;
+    p->PPTm = p->PPT;
+    p->ntile_m = p->ntile;
+
+    // partial-buffer offsets
+    p->gbase.assign(K + 1, 0);
+    p->mbase.assign(K + 1, 0);
+    for (int k = 0; k < K; k++) {
+        const long long d = p->fptr[k + 1] - p->fptr[k];
+        const bool owned = k >= p->k_lo && k < p->k_hi;
+        const long long rec = owned ? d * (d + 1) / 2 * 36 + 6 * d : 0;
+        p->gbase[k + 1] = p->gbase[k] + rec * p->ntile;
+        p->mbase[k + 1] = p->mbase[k] + (owned ? d * (d + 1) / 2 * 36 : 0);
+    }
+
+    // workspace layout
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes);
+        return o;
+    };
+    p->off_kx = take(sizeof(int) * K);
+    p->off_fptr = take(sizeof(int) * (K + 1));
+    p->off_fedge = take(sizeof(int) * std::max<int64_t>(E, 1));
+    p->off_ejj = take(sizeof(int) * std::max<int64_t>(E, 1));
+    p->off_gbase = take(sizeof(long long) * (K + 1));
+    p->off_mbase = take(sizeof(long long) * (K + 1));
+    p->idx_bytes = off;
+    p->off_epart = take(sizeof(float) * (size_t)std::max<int64_t>(E, 1) * p->ntile * kEdgeStride);
+    p->off_gpart = take(sizeof(float) * (size_t)std::max<long long>(p->gbase[K], 1));
+    p->off_msc = take(sizeof(double) * (size_t)std::max<long long>(p->mbase[K], 1));
+    p->off_q = take(sizeof(float) * (size_t)K * p->HW);
+    p->off_qw = take(sizeof(float) * (size_t)K * p->HW);
+    p->off_sys = take(sizeof(double) * ((size_t)p->npad * p->npad + p->npad));
+    p->off_dx = take(sizeof(float) * (size_t)p->npad);
+    p->off_flag = take(256);
+    p->total = off;
+
+    p->blob.assign(p->idx_bytes, 0);
+    std::memcpy(p->blob.data() + p->off_kx, p->kx32.data(), sizeof(int) * K);
+    std::memcpy(p->blob.data() + p->off_fptr, p->fptr.data(), sizeof(int) * (K + 1));
+    if (E > 0) {
+        std::memcpy(p->blob.data() + p->off_fedge, p->fedge.data(), sizeof(int) * E);
+        std::memcpy(p->blob.data() + p->off_ejj, p->e_jj.data(), sizeof(int) * E);
+    }
+    std::memcpy(p->blob.data() + p->off_gbase, p->gbase.data(), sizeof(long long) * (K + 1));
+    std::memcpy(p->blob.data() + p->off_mbase, p->mbase.data(), sizeof(long long) * (K + 1));
+    *out = p;
+    return 0;
+}
+
+extern "C" void vipe_ba_plan_destroy(vipe_ba_plan *plan) { delete plan; }
+extern "C" int64_t vipe_ba_plan_num_kx(const vipe_ba_plan *p) { return p ? p->K : -1; }
+extern "C" int vipe_ba_plan_copy_kx(const vipe_ba_plan *p, int64_t *o) {
+    if (!p || !o) return fail("null argument");
+    std::copy(p->kx.begin(), p->kx.end(), o);
+    return 0;
+}
+extern "C" int vipe_ba_plan_copy_kk_exp(const vipe_ba_plan *p, int64_t *o) {
+    if (!p || !o) return fail("null argument");
+    std::copy(p->kk_exp.begin(), p->kk_exp.end(), o);
+    return 0;
+}
+extern "C" int vipe_ba_plan_copy_csr(const vipe_ba_plan *p, int64_t *ptrs, int64_t *idxs) {
+    if (!p || !ptrs || !idxs) return fail("null argument");
+    for (int k = 0; k <= p->K; k++) ptrs[k] = p->fptr[k];
+    for (int64_t e = 0; e < p->E; e++) idxs[e] = p->fedge[e];
+    return 0;
+}
+extern "C" int vipe_ba_plan_owned_range(const vipe_ba_plan *p, int rank, int64_t *lo, int64_t *hi) {
+    if (!p || !lo || !hi || rank < 0 || rank >= p->world) return fail("bad argument");
+    *lo = p->own_lo[rank];
+    *hi = p->own_hi[rank];
+    return 0;
+}
+extern "C" int64_t vipe_ba_plan_num_schur_triples(const vipe_ba_plan *p) { return p ? p->n_triples : -1; }
+extern "C" int vipe_ba_plan_max_degree(const vipe_ba_plan *p) { return p ? p->dmax : -1; }
+extern "C" size_t vipe_ba_workspace_bytes(const vipe_ba_plan *p) { return p ? p->total : 0; }
+extern "C" int64_t vipe_ba_launch_count(const vipe_ba_plan *p) { return p ? p->launches : -1; }
+
+extern "C" int vipe_ba_plan_upload(const vipe_ba_plan *p, void *ws, void *stream) {
+    if (!p || !ws) return fail("null argument");
+    VBA_CUDA(cudaMemcpyAsync(ws, p->blob.data(), p->idx_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+static Tables make_tables(const vipe_ba_plan *p, void *ws) {
+    unsigned char *w = (unsigned char *)ws;
+    Tables tb;
+    tb.kx = (const int *)(w + p->off_kx);
+    tb.fptr = (const int *)(w + p->off_fptr);
+    tb.fedge = (const int *)(w + p->off_fedge);
+    tb.e_jj = (const int *)(w + p->off_ejj);
+    tb.gbase = (const long long *)(w + p->off_gbase);
+    tb.mbase = (const long long *)(w + p->off_mbase);
+    tb.K = p->K;
+    tb.E = (int)p->E;
+    tb.N = (int)p->N;
+    tb.HW = p->HW;
+    tb.wd = p->wd;
+    tb.t0 = p->t0;
+    tb.t1 = p->t1;
+    tb.P = p->P;
+    tb.ntile = p->ntile;
+    tb.k_lo = p->k_lo;
+    tb.k_hi = p->k_hi;
+    return tb;
+}
+
+extern "C" void *vipe_ba_system_buffer(const vipe_ba_plan *p, void *ws, int64_t *n_out, int64_t *count_out) {
+    if (!p || !ws) return nullptr;
+    if (n_out) *n_out = p->npad;
+    if (count_out) *count_out = (int64_t)p->npad * p->npad + p->npad;
+    return (unsigned char *)ws + p->off_sys;
+}
+extern "C" float *vipe_ba_debug_q(const vipe_ba_plan *p, void *ws) { return (float *)((unsigned char *)ws + p->off_q); }
+extern "C" float *vipe_ba_debug_qw(const vipe_ba_plan *p, void *ws) { return (float *)((unsigned char *)ws + p->off_qw); }
+
+static int check_tensors(const vipe_ba_plan *p, const vipe_ba_tensors *t, int motion_only) {
+    if (!p || !t) return fail("null plan/tensors");
+    if (!t->poses || !t->disps || !t->intrinsics || !t->targets || !t->weights || !t->dx_out)
+        return fail("null tensor pointer");
+    if (!motion_only && (!t->disps_sens || !t->eta || !t->dz_out)) return fail("disps_sens/eta/dz_out required unless motion_only");
+    return 0;
+}
+
+extern "C" int vipe_ba_linearize(const vipe_ba_plan *p, const vipe_ba_tensors *t, void *ws, int motion_only,
+                                 void *stream) {
+    if (check_tensors(p, t, motion_only)) return 1;
+    if (!ws) return fail("null workspace");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char *w = (unsigned char *)ws;
+    double *H = (double *)(w + p->off_sys);
+    double *b = H + (size_t)p->npad * p->npad;
+    VBA_CUDA(launch_system_clear(H, b, p->n, p->npad, st));
+    p->launches += (p->npad > p->n) ? 2 : 1;
+    const int nframes = p->k_hi - p->k_lo;
+    if (nframes <= 0 || p->P <= 0) return 0;
+
+    LinArgs la;
+    la.tb = make_tables(p, ws);
+    la.poses = t->poses;
+    la.disps = t->disps;
+    la.intr = t->intrinsics;
+    la.dsens = t->disps_sens;
+    la.targets = t->targets;
+    la.weights = t->weights;
+    la.eta = t->eta;
+    la.epart = (float *)(w + p->off_epart);
+    la.gpart = (float *)(w + p->off_gpart);
+    la.qbuf = (float *)(w + p->off_q);
+    la.qwbuf = (float *)(w + p->off_qw);
+    VBA_CUDA(launch_linearize(la, nframes, std::max(p->dmax, 1), motion_only != 0, p->NT, p->PPT, st));
+    p->launches++;
+
+    ReduceArgs ra;
+    ra.tb = la.tb;
+    ra.poses = t->poses;
+    ra.epart = la.epart;
+    ra.gpart = la.gpart;
+    ra.msc = (double *)(w + p->off_msc);
+    ra.hsys = H;
+    ra.bsys = b;
+    ra.n = p->npad;
+    ra.motion_only = motion_only;
+    VBA_CUDA(launch_frame_reduce(ra, nframes, std::max(p->dmax, 1), st));
+    p->launches++;
+    return 0;
+}
+
+extern "C" int vipe_ba_solve_update(const vipe_ba_plan *p, const vipe_ba_tensors *t, void *ws, float lm, float ep,
+                                    int motion_only, void *stream) {
+    if (check_tensors(p, t, motion_only)) return 1;
+    if (!ws) return fail("null workspace");
+    if (p->P <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char *w = (unsigned char *)ws;
+    double *H = (double *)(w + p->off_sys);
+    double *b = H + (size_t)p->npad * p->npad;
+    int *flag = (int *)(w + p->off_flag);
+    int cnt = 0;
+    VBA_CUDA(launch_damped_solve(H, b, p->n, p->npad, lm, ep, t->dx_out, flag, st, &cnt));
+    p->launches += cnt;
+    const int nframes = p->k_hi - p->k_lo;
+    if (!motion_only && nframes > 0) {
+        BackArgs ba;
+        ba.tb = make_tables(p, ws);
+        ba.poses = t->poses;
+        ba.intr = t->intrinsics;
+        ba.weights = t->weights;
+        ba.disps = t->disps;
+        ba.qbuf = (const float *)(w + p->off_q);
+        ba.qwbuf = (const float *)(w + p->off_qw);
+        ba.dx = t->dx_out;
+        ba.dz_out = t->dz_out;
+        VBA_CUDA(launch_backsub(ba, nframes, std::max(p->dmax, 1), st));
+        p->launches++;
+    }
+    VBA_CUDA(launch_pose_retr(t->poses, t->dx_out, p->t0, p->t1, st));
+    p->launches++;
+    return 0;
+}
+
+extern "C" int vipe_ba_run(const vipe_ba_plan *p, const vipe_ba_tensors *t, void *ws, int iterations, float lm,
+                           float ep, int motion_only, void *stream) {
+    if (!p) return fail("null plan");
+    if (p->world != 1) return fail("vipe_ba_run needs a single-rank plan; use linearize/solve_update with an all-reduce");
+    p->launches = 0;
+    for (int it = 0; it < iterations; it++) {
+        if (vipe_ba_linearize(p, t, ws, motion_only, stream)) return 1;
+        if (vipe_ba_solve_update(p, t, ws, lm, ep, motion_only, stream)) return 1;
+    }
+    return 0;
+}

@@ -1,0 +1,177 @@
+// Shared declarations of the dense-BA kernels (sm_100a).  See DESIGN.md for the data layout.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vba {
+
+constexpr float kMinDepth = 0.25f;      // reference: geom_kernels.cu:33
+constexpr float kWeightScale = 0.001f;  // reference: geom_kernels.cu:304-305
+constexpr float kAlpha = 0.05f;         // reference: geom_kernels.cu:1359
+constexpr float kStereoBaseline = -0.1f;  // reference: geom_kernels.cu:222
+
+constexpr int kEdgeVals = 27;    // 20 unique non-zero entries of H_jj, 6 of v_j, 1 energy
+constexpr int kEdgeStride = 28;  // padded stride of the per-(edge,tile) partial record
+constexpr int kEcStride = 16;    // floats per edge constant record in shared memory
+
+// Index tables + sizes shared by every kernel of one plan (device pointers live in the workspace head).
+struct Tables {
+    const int *kx;      // [K]   source-frame id of kx position k
+    const int *fptr;    // [K+1] CSR of edges by source frame (slots)
+    const int *fedge;   // [E]   slot -> edge id
+    const int *e_jj;    // [E]   edge id -> target frame
+    const long long *gbase;  // [K+1] float offset of frame k's Gram partials (already multiplied by ntile)
+    const long long *mbase;  // [K+1] double offset of frame k's M scratch
+    int K, E, N, HW, wd, t0, t1, P, ntile, k_lo, k_hi;
+};
+
+struct LinArgs {
+    Tables tb;
+    const float *poses, *disps, *intr, *dsens, *targets, *weights, *eta;
+    float *epart;  // [E_slots][ntile][kEdgeStride]
+    float *gpart;  // per frame: [ntile][npairs*36 + 6*d]
+    float *qbuf;   // [K][HW]  Q = 1/C
+    float *qwbuf;  // [K][HW]  Q*w
+};
+
+struct ReduceArgs {
+    Tables tb;
+    const float *poses;
+    const float *epart, *gpart;
+    double *msc;   // M scratch
+    double *hsys;  // [n*n] row-major, lower triangle (+ full diagonal blocks)
+    double *bsys;  // [n]
+    int n;
+    int motion_only;
+};
+
+struct BackArgs {
+    Tables tb;
+    const float *poses, *intr, *weights;
+    float *disps;
+    const float *qbuf, *qwbuf;
+    const float *dx;  // [P][6] fp32
+    float *dz_out;    // [K][HW]
+};
+
+// ------------------------------------------------------------------------------------------------
+// per-edge relative pose.  Same algebra as relSE3/actSO3 (geom_kernels.cu:69-114) written as a matrix:
+// actSO3(q, X) = X + 2w (v x X) + 2 v x (v x X) is linear in X for ANY q (unit or not), and its matrix is
+// the usual quaternion rotation matrix.  T is float or double.
+template <typename T>
+struct RelPose {
+    T R[9];
+    T t[3];
+    bool stereo;
+};
+
+template <typename T>
+__device__ __forceinline__ void quat_to_mat(const T *q, T *R) {
+    const T x = q[0], y = q[1], z = q[2], w = q[3];
+    R[0] = T(1) - T(2) * (y * y + z * z);
+    R[1] = T(2) * (x * y - w * z);
+    R[2] = T(2) * (x * z + w * y);
+    R[3] = T(2) * (x * y + w * z);
+    R[4] = T(1) - T(2) * (x * x + z * z);
+    R[5] = T(2) * (y * z - w * x);
+    R[6] = T(2) * (x * z - w * y);
+    R[7] = T(2) * (y * z + w * x);
+    R[8] = T(1) - T(2) * (x * x + y * y);
+}
+
+template <typename T>
+__device__ __forceinline__ void relative_pose(const float *__restrict__ poses, int i, int j, RelPose<T> &rp) {
+    rp.stereo = (i == j);
+    if (rp.stereo) {  // geom_kernels.cu:219-230
+        rp.R[0] = rp.R[4] = rp.R[8] = T(1);
+        rp.R[1] = rp.R[2] = rp.R[3] = rp.R[5] = rp.R[6] = rp.R[7] = T(0);
+        rp.t[0] = T(kStereoBaseline);
+        rp.t[1] = rp.t[2] = T(0);
+        return;
+    }
+    T ti[3], qi[4], tj[3], qj[4], qij[4];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        ti[k] = T(poses[7 * i + k]);
+        tj[k] = T(poses[7 * j + k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        qi[k] = T(poses[7 * i + 3 + k]);
+        qj[k] = T(poses[7 * j + 3 + k]);
+    }
+    // qij = qj * conj(qi)   (geom_kernels.cu:105-108)
+    qij[0] = -qj[3] * qi[0] + qj[0] * qi[3] - qj[1] * qi[2] + qj[2] * qi[1];
+    qij[1] = -qj[3] * qi[1] + qj[1] * qi[3] - qj[2] * qi[0] + qj[0] * qi[2];
+    qij[2] = -qj[3] * qi[2] + qj[2] * qi[3] - qj[0] * qi[1] + qj[1] * qi[0];
+    qij[3] = qj[3] * qi[3] + qj[0] * qi[0] + qj[1] * qi[1] + qj[2] * qi[2];
+    quat_to_mat(qij, rp.R);
+    // tij = tj - Rij ti   (geom_kernels.cu:110-113)
+#pragma unroll
+    for (int k = 0; k < 3; k++) rp.t[k] = tj[k] - (rp.R[3 * k] * ti[0] + rp.R[3 * k + 1] * ti[1] + rp.R[3 * k + 2] * ti[2]);
+}
+
+// G (6x6, row-major) with J_i = G J_j, i.e. G = -M where M X = adjSE3(tij, qij, X) (geom_kernels.cu:88-102,332-333):
+//   M = [[R^T, 0], [-R^T [t]x, R^T]]   =>   G = [[-R^T, 0], [R^T [t]x, -R^T]]
+template <typename T>
+__device__ __forceinline__ void adjoint_G(const RelPose<T> &rp, T *G) {
+    const T *R = rp.R;
+    const T *t = rp.t;
+    // [t]x
+    const T tx[9] = {T(0), -t[2], t[1], t[2], T(0), -t[0], -t[1], t[0], T(0)};
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const T rt = R[3 * c + r];  // R^T[r][c]
+            G[6 * r + c] = -rt;
+            G[6 * r + 3 + c] = T(0);
+            G[6 * (r + 3) + 3 + c] = -rt;
+            // (R^T [t]x)[r][c] = sum_k R[k][r] * tx[k][c]
+            G[6 * (r + 3) + c] = R[0 + r] * tx[0 + c] + R[3 + r] * tx[3 + c] + R[6 + r] * tx[6 + c];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp "transpose" reductions: V values live in every lane; afterwards lane l holds the sum over all
+// 32 lanes of value (l mod V).  Costs V-1 (+ log2(32/V)) shuffles instead of 5V.
+template <int V>
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[V], int lane) {
+    static_assert(V == 32 || V == 16 || V == 8 || V == 4 || V == 2, "power of two");
+#pragma unroll
+    for (int s = V / 2; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; i++) {
+            const float send = up ? v[i] : v[i + s];
+            const float keep = up ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    float r = v[0];
+#pragma unroll
+    for (int s = V; s < 32; s <<= 1) r += __shfl_xor_sync(0xffffffffu, r, s);
+    return r;
+}
+
+// decode pair index p -> (m, mp) with m <= mp, p = mp*(mp+1)/2 + m
+__device__ __forceinline__ void decode_pair(int p, int &m, int &mp) {
+    int c = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+    while ((c + 1) * (c + 2) / 2 <= p) c++;
+    while (c * (c + 1) / 2 > p) c--;
+    mp = c;
+    m = p - c * (c + 1) / 2;
+}
+
+// position of the non-zero unique entries of H_jj (lower triangle, (1,0) is structurally zero) in the
+// 27-value record:  slot(r,c) for r >= c.
+__host__ __device__ __forceinline__ int hslot(int r, int c) {
+    // order: (0,0) (1,1) (2,0) (2,1) (2,2) (3,0) (3,1) (3,2) (3,3) (4,0)..(4,4) (5,0)..(5,5)
+    if (r == 0) return 0;
+    if (r == 1) return c == 1 ? 1 : -1;
+    return 2 + (r * (r + 1) / 2 - 3) + c;  // r=2 -> base 2, r=3 -> 5, r=4 -> 9, r=5 -> 14
+}
+
+}  // namespace vba

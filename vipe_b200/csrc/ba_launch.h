@@ -1,0 +1,29 @@
+// Host-side launcher declarations shared between the kernel translation units and the C ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "ba_common.cuh"
+
+namespace vba {
+
+// choose the (threads, pixels-per-thread) tile shape of the frame kernels for a given max degree
+bool tile_config(int HW, int dmax, bool motion, int &NT, int &PPT);
+
+cudaError_t launch_linearize(const LinArgs &a, int nframes, int dmax, bool motion, int NT, int PPT, cudaStream_t st);
+cudaError_t launch_frame_reduce(const ReduceArgs &a, int nframes, int dmax, cudaStream_t st);
+cudaError_t launch_backsub(const BackArgs &a, int nframes, int dmax, cudaStream_t st);
+cudaError_t launch_pose_retr(float *poses, const float *dx, int t0, int t1, cudaStream_t st);
+
+// Dense damped Cholesky solve of the reduced camera system (chol.cu).
+//   H: [npad x npad] fp64 row-major, lower triangle valid on entry (destroyed);  b: [npad] fp64 (destroyed)
+//   diag += ep + lm*diag (geom_kernels.cu:1176); factor; solve; dx[n] fp32.  Failure => dx = 0 (:1186-1188).
+// Returns the number of kernels launched through *launches.
+cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx, int *flag,
+                                cudaStream_t st, int *launches);
+// zero [H ; b] and put the identity on the padded diagonal
+cudaError_t launch_system_clear(double *H, double *b, int n, int npad, cudaStream_t st);
+
+constexpr int kCholBlock = 64;
+
+}  // namespace vba

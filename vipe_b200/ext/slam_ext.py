@@ -1,0 +1,114 @@
+"""`slam_ext` -- host-side mirror of the reference operator module for the dense-BA hot path.
+
+Reference interface: `vipe.ext.slam_ext.ba` (vipe/ext/__init__.py:43), bound by
+csrc/slam_ext/slam.cpp:24-27,32 to `ba_cuda` (csrc/slam_ext/geom_kernels.cu:1283-1404).
+Same positional signature, same tensor layouts, same in-place update of `poses` and `disps`, same
+`[dx, dz]` return, same RuntimeError on non-contiguous inputs.  Underneath it is a ctypes call into
+libvipe_ba.so (include/vipe_ba.h); torch only supplies device memory and the current stream.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .. import _lib
+from ..plan import BAPlan, cached_plan
+
+__all__ = ["ba", "ba_plan"]
+
+
+def _check_contiguous(**tensors):
+    for name, t in tensors.items():
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} must be contiguous")  # CHECK_CONTIGUOUS, geom_kernels.cu:30,1287-1294
+
+
+def _check_dtype(dtype, **tensors):
+    for name, t in tensors.items():
+        if t.dtype != dtype:
+            raise RuntimeError(f"expected scalar type {dtype} for {name} but found {t.dtype}")
+
+
+def ba_plan(ii: torch.Tensor, jj: torch.Tensor, n_frames: int, ht: int, wd: int, t0: int, t1: int) -> BAPlan:
+    """Build (or fetch from the cache) the index bookkeeping for a graph; `ba` does this implicitly."""
+    return cached_plan(ii.detach().to("cpu", torch.int64).contiguous(), jj.detach().to("cpu", torch.int64).contiguous(),
+                       n_frames, ht, wd, t0, t1)
+
+
+def _tensors(poses, disps, intrinsics, disps_sens, targets, weights, eta, dx, dz, motion_only):
+    t = _lib.Tensors()
+    t.poses = poses.data_ptr()
+    t.disps = disps.data_ptr()
+    t.intrinsics = intrinsics.data_ptr()
+    t.disps_sens = disps_sens.data_ptr()
+    t.targets = targets.data_ptr()
+    t.weights = weights.data_ptr()
+    t.eta = None if (motion_only and eta is None) else eta.data_ptr()
+    t.dx_out = dx.data_ptr()
+    t.dz_out = dz.data_ptr() if dz is not None else None
+    return t
+
+
+def validate(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, t1, motion_only):
+    """Checks of the reference (contiguity) plus the shape/device checks it omits."""
+    _check_contiguous(targets=targets, weights=weights, poses=poses, disps=disps, intrinsics=intrinsics,
+                      disps_sens=disps_sens, ii=ii, jj=jj)
+    _check_dtype(torch.float32, targets=targets, weights=weights, poses=poses, disps=disps, intrinsics=intrinsics,
+                 disps_sens=disps_sens)
+    _check_dtype(torch.int64, ii=ii, jj=jj)
+    dev = poses.device
+    if dev.type != "cuda":
+        raise RuntimeError("slam_ext.ba needs CUDA tensors (vipe_b200 has no CPU fallback)")
+    for name, t in dict(disps=disps, intrinsics=intrinsics, disps_sens=disps_sens, targets=targets, weights=weights,
+                        ii=ii, jj=jj).items():
+        if t.device != dev:
+            raise RuntimeError(f"{name} is on {t.device}, poses on {dev}")
+    if poses.dim() != 2 or poses.shape[1] != 7:
+        raise RuntimeError("poses must be [N,7]")
+    if disps.dim() != 3 or disps.shape[0] != poses.shape[0]:
+        raise RuntimeError("disps must be [N,ht,wd]")
+    N, ht, wd = disps.shape
+    E = ii.numel()
+    if disps_sens.shape != disps.shape:
+        raise RuntimeError("disps_sens must have the shape of disps")
+    if tuple(targets.shape) != (E, 2, ht, wd) or tuple(weights.shape) != (E, 2, ht, wd):
+        raise RuntimeError("targets/weights must be [E,2,ht,wd] (channel-first, geom_kernels.cu:308-309)")
+    if intrinsics.numel() != 4:
+        raise RuntimeError("intrinsics must hold 4 values (fx, fy, cx, cy)")
+    if not (0 <= t0 <= t1 <= N):
+        raise RuntimeError("need 0 <= t0 <= t1 <= N")
+    return dev, N, ht, wd, E
+
+
+def ba(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, t1, iterations, lm, ep, motion_only):
+    """Dense bundle adjustment; drop-in for `vipe.ext.slam_ext.ba` (csrc/slam_ext/slam.cpp:24-27).
+
+    Runs `iterations` Gauss-Newton steps on the device without host synchronisation inside the loop, updates
+    `poses[t0:t1]` and `disps[kx]` in place and returns `[dx, dz]` of the last iteration
+    (`dx[t1-t0, 6]`, `dz[K, ht*wd]`; `dz` is an empty tensor when `motion_only`, where the reference returns an
+    undefined one)."""
+    t0, t1, iterations = int(t0), int(t1), int(iterations)
+    dev, N, ht, wd, E = validate(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, t1, motion_only)
+    motion_only = bool(motion_only)
+    plan = ba_plan(ii, jj, N, ht, wd, t0, t1)  # one D2H of the edge list per call (the reference does >= 12 per iteration)
+    K, HW, P = plan.K, ht * wd, t1 - t0
+    dx = torch.zeros(P, 6, dtype=torch.float32, device=dev)
+    dz = None
+    if not motion_only:
+        if eta.dtype != torch.float32:
+            raise RuntimeError(f"expected scalar type torch.float32 for eta but found {eta.dtype}")
+        if eta.numel() != K * HW:
+            raise RuntimeError(f"eta must be viewable as [K={K}, ht*wd] (geom_kernels.cu:1365), got {tuple(eta.shape)}")
+        eta = eta.contiguous()
+        dz = torch.zeros(K, HW, dtype=torch.float32, device=dev)
+    if iterations <= 0 or P <= 0:
+        return [dx, dz if dz is not None else torch.empty(0, device=dev)]
+    with torch.cuda.device(dev):
+        ws = plan.workspace(dev)
+        tens = _tensors(poses, disps, intrinsics, disps_sens, targets, weights, eta, dx, dz, motion_only)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.lib().vipe_ba_run(plan.handle, C.byref(tens), ws.data_ptr(), iterations, float(lm), float(ep),
+                                          int(motion_only), stream), "vipe_ba_run")
+    return [dx, dz if dz is not None else torch.empty(0, device=dev)]

@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- dense bundle adjustment throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|c5]
+
+A "step" is one full `slam_ext.ba` call (all Gauss-Newton iterations of the workload) on one synthetic
+problem.  Default workload: C3, the backend global BA (300 keyframes, 3000 edges, 48x64, 8 iterations,
+lm=1e-5, ep=1e-2) -- the configuration BASELINE.json quotes "at 1/2/4/8 B200".  With N > 1 the same problem
+is sharded by source keyframe over the ranks (strong scaling; one all-reduce of the reduced camera system
+per iteration).  Prints ONE JSON line on rank 0.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "dense_ba_gn_iterations_per_sec"
+UNIT = "iter/s"
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.is_file():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 7 for i in range(4) if s[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def algorithmic_bytes(cfg, E, K, N, HW, motion_only):
+    """unique compulsory bytes of one GN iteration, and of the linearise kernel alone."""
+    if motion_only:
+        it = 16 * E * HW + 4 * K * HW + 56 * N + 16 * E
+        lin = 16 * E * HW + 4 * K * HW + 28 * N + 8 * E
+    else:
+        it = 16 * E * HW + 16 * K * HW + 56 * N + 16 * E
+        lin = 16 * E * HW + 12 * K * HW + 28 * N + 8 * E  # targets+weights, disps+disps_sens+eta, poses, edge list
+    return it, lin
+
+
+def cpu_baseline(pr, seconds_budget=25.0):
+    """fp32 twin of the oracle (pure torch CPU ops, same math as ba_cuda) on a bounded sample of the workload."""
+    from oracle import ba_oracle
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = pr.cfg
+    a = pr.args()
+    a[11] = 1
+    t = time.perf_counter()
+    ba_oracle.ba(*a, dtype=torch.float32)
+    t1 = time.perf_counter() - t
+    iters = max(1, min(cfg.iters, int(seconds_budget / max(t1, 1e-6))))
+    a = pr.args()
+    a[11] = iters
+    t = time.perf_counter()
+    ba_oracle.ba(*a, dtype=torch.float32)
+    dt = time.perf_counter() - t
+    return {"value": iters / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{cfg.name}: one ba call of {iters} GN iteration(s) of the full problem, fp32 torch CPU ops, after a 1-iteration warm-up"}
+
+
+def run_reference(args, pr):
+    """--impl reference: the reference's own slam_ext.ba (CUDA kernels + its host Schur/solve code, compiled
+    unmodified from /root/reference with oracle/eigen_stub standing in for Eigen) on the same config; if that build
+    is absent, the torch CPU port of the same algorithm."""
+    from oracle import build_ref
+
+    cfg = pr.cfg
+    sample_iters = min(cfg.iters, 2)
+    mod = build_ref.load() if torch.cuda.is_available() else None
+    HW = cfg.ht * cfg.wd
+    E = pr.ii.numel()
+    if mod is not None:
+        dev = torch.device("cuda:0")
+        base = pr.args(dev)
+
+        def step():
+            a = [x.clone() if torch.is_tensor(x) and i < 2 else x for i, x in enumerate(base)]
+            a[11] = sample_iters
+            mod.slam_ext.ba(*a)
+
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t
+        kind, cores = "reference", os.cpu_count()
+        sample = (f"{cfg.name}: {args.steps} ba calls of {sample_iters} GN iterations each (full problem), reference CUDA kernels on "
+                  f"one B200 + reference host Schur/solve code on the host cores (dense-LLT Eigen stand-in), wall clock")
+    else:
+        from oracle import ba_oracle
+
+        torch.set_num_threads(os.cpu_count() or 1)
+
+        def step():
+            a = pr.args()
+            a[11] = sample_iters
+            ba_oracle.ba(*a, dtype=torch.float32)
+
+        steps = max(1, min(args.steps, 3))
+        step()
+        t = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = time.perf_counter() - t
+        args.steps = steps
+        kind, cores = "port", torch.get_num_threads()
+        sample = f"{cfg.name}: {steps} ba calls of {sample_iters} GN iterations each, fp32 torch CPU port of ba_cuda"
+    value = args.steps * sample_iters / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "edge_pixels_per_sec": value * E * HW,
+            "config": {"workload": workload_name(cfg), "frames": cfg.n_frames, "edges": E, "ht": cfg.ht, "wd": cfg.wd,
+                       "gn_iterations_per_step": sample_iters, "lm": cfg.lm, "ep": cfg.ep, "motion_only": cfg.motion_only},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(cfg):
+    names = {"c1": "C1 synthetic dense BA: 8 keyframes, 24 edges, 48x64, 2 GN iters",
+             "c2": "C2 frontend local BA window: 16 keyframes, 120 edges, 48x64, 4 GN iters",
+             "c3": "C3 backend global BA: 300 keyframes, 3000 edges, 48x64, 8 GN iters",
+             "c4": "C4 large global BA: 1000 keyframes, 12000 edges, 64x112, 8 GN iters",
+             "c5": "C5 motion-only BA: 64 clips x (16 keyframes, 120 edges, 48x64), 4 GN iters"}
+    return names[cfg.name]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from vipe_b200.synthetic import CONFIGS, make_problem
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        run_reference(args, make_problem(args.workload))
+        return
+
+    from vipe_b200.distributed import ba_sharded
+    from vipe_b200.ext import slam_ext
+    from vipe_b200 import _lib
+    import ctypes as C
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = CONFIGS[args.workload]
+    clips = cfg.clips
+    # C5: the 64 clips are independent -> each rank takes its share of the clips (replicas, no collective)
+    my_clips = list(range(rank, clips, world)) if clips > 1 else [0]
+    problems = [make_problem(cfg, clip=c) for c in my_clips]
+    pr = problems[0]
+    HW, E, N = cfg.ht * cfg.wd, pr.ii.numel(), cfg.n_frames
+    sharded = world > 1 and clips == 1
+
+    dev_args = [p.args(dev) for p in problems]
+    init_state = [(a[0].clone(), a[1].clone()) for a in dev_args]
+    plans = [slam_ext.ba_plan(p.ii, p.jj, N, cfg.ht, cfg.wd, p.t0, p.t1) for p in problems] if not sharded else []
+    K = int(torch.unique(torch.cat([torch.arange(pr.t0, pr.t1), pr.ii])).numel())
+
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def reset():
+        for a, (p0, d0) in zip(dev_args, init_state):
+            a[0].copy_(p0)
+            a[1].copy_(d0)
+
+    def step():
+        for a in dev_args:
+            if sharded:
+                ba_sharded(*a, exchange=True)
+            else:
+                slam_ext.ba(*a)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        reset()
+        step()
+    barrier()
+    for pl in plans:
+        _lib.check(_lib.lib().vipe_ba_profile_enable(pl.handle, 1), "profile_enable")
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage_ms = [0.0, 0.0, 0.0, 0.0]
+    stage_iters = 0
+    barrier()
+    wall0 = time.perf_counter()
+    for s in range(args.steps):
+        reset()
+        flush_buf.zero_()  # L2 flush between timed steps (outside the event bracket)
+        ev[s][0].record()
+        step()
+        ev[s][1].record()
+        if plans:
+            torch.cuda.synchronize()
+            for pl in plans:
+                ms4, its = (C.c_float * 4)(), C.c_int()
+                _lib.check(_lib.lib().vipe_ba_profile_read(pl.handle, C.byref(ms4), C.byref(its)), "profile_read")
+                stage_ms = [x + y for x, y in zip(stage_ms, ms4)]
+                stage_iters += its.value
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    launches = sum(pl.launch_count for pl in plans) * args.steps if plans else None
+
+    iters_total = args.steps * cfg.iters * clips
+    value = iters_total / (total_ms / 1e3)
+    edge_px = E * HW
+    it_bytes, lin_bytes = algorithmic_bytes(cfg, E, K, N, HW, cfg.motion_only)
+    peak, peak_src = measured_peaks()
+
+    roofline = None
+    if stage_iters > 0:
+        lin_ms = stage_ms[0] / stage_iters  # average duration of one linearise launch (incl. the system clear)
+        achieved = lin_bytes / (lin_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "vba::linearize_kernel (per-source-frame Jacobian/Hessian + Schur Gram)",
+                    "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "algorithmic_bytes_per_launch": lin_bytes, "avg_launch_ms": lin_ms,
+                    "stage_ms_per_iteration": {"linearize_schur": stage_ms[0] / stage_iters, "assemble": stage_ms[1] / stage_iters,
+                                               "solve": stage_ms[2] / stage_iters, "backsub_retract": stage_ms[3] / stage_iters},
+                    "whole_iteration": {"algorithmic_bytes": it_bytes,
+                                        "achieved_gbs": it_bytes * cfg.iters * clips * args.steps / (total_ms * 1e-3) / 1e9 / max(world, 1)}}
+        prof = ROOT / "profiles" / "traffic.json"
+        if prof.is_file():
+            try:
+                roofline["traffic"] = json.loads(prof.read_text()).get(args.workload, {}).get("linearize_dram_bytes_per_launch")
+            except Exception:
+                pass
+
+    # end-to-end through the public API with host buffers (rank-local inputs in pinned memory)
+    host_args = [[x.pin_memory() if torch.is_tensor(x) else x for x in p.args()] for p in problems]
+    h2d = sum(x.numel() * x.element_size() for x in host_args[0] if torch.is_tensor(x)) * len(problems)
+    d2h = (host_args[0][0].numel() + host_args[0][1].numel()) * 4 * len(problems)
+    out_host = [(torch.empty_like(h[0]).pin_memory(), torch.empty_like(h[1]).pin_memory()) for h in host_args]
+
+    def e2e_step():
+        for h, (op, od) in zip(host_args, out_host):
+            a = [x.to(dev, non_blocking=True) if torch.is_tensor(x) else x for x in h]
+            if sharded:
+                ba_sharded(*a, exchange=True)
+            else:
+                slam_ext.ba(*a)
+            op.copy_(a[0], non_blocking=True)
+            od.copy_(a[1], non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = e2e_steps * cfg.iters * clips / (e2e_ms / 1e3)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if clips == 1 else "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "edge_pixels_per_sec": value * edge_px,
+                "config": {"workload": workload_name(cfg), "frames": N, "edges": E, "ht": cfg.ht, "wd": cfg.wd,
+                           "gn_iterations_per_step": cfg.iters, "lm": cfg.lm, "ep": cfg.ep, "motion_only": cfg.motion_only,
+                           "clips": clips, "parallelism": f"keyframe-sharded x{world}" if sharded else ("clip-replicas" if clips > 1 else "single"),
+                           "l2": "flushed between timed steps (256 MB write)", "timing": "cuda events per step, max over ranks",
+                           "wall_s_timed_region": wall},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(pr)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

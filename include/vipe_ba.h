@@ -105,6 +105,15 @@ void *vipe_ba_system_buffer(const vipe_ba_plan *plan, void *workspace, int64_t *
 /* Test hooks: DEV fp32 [K,HW] buffers written by the last linearize (Q = 1/C and Q*w of geom_kernels.cu:1365-1370). */
 float *vipe_ba_debug_q(const vipe_ba_plan *plan, void *workspace);
 float *vipe_ba_debug_qw(const vipe_ba_plan *plan, void *workspace);
+/*
+ * Optional per-stage timing (tracing hook).  When enabled, vipe_ba_run records CUDA events on the run's stream
+ * around each stage of each iteration (linearise+Schur | assemble | solve | back-substitute+retract).  After the
+ * caller has synchronised the stream, vipe_ba_profile_read returns the summed milliseconds per stage of the last
+ * run and the number of iterations they cover.
+ */
+int vipe_ba_profile_enable(vipe_ba_plan *plan, int on);
+int vipe_ba_profile_read(const vipe_ba_plan *plan, float ms_out[4], int *iterations_out);
+
 /* Number of kernels the last vipe_ba_run / linearize+solve_update pair enqueued (for bench.py's gpu_launches). */
 int64_t vipe_ba_launch_count(const vipe_ba_plan *plan);
 

@@ -44,7 +44,15 @@ struct vipe_ba_plan {
     size_t total = 0;
     std::vector<unsigned char> blob;  // host image of the index tables
     mutable int64_t launches = 0;
+    // optional stage timing
+    bool profile = false;
+    mutable std::vector<cudaEvent_t> events;  // 5 per iteration
+    mutable int prof_iters = 0;
+    ~vipe_ba_plan() {
+        for (auto e : events) cudaEventDestroy(e);
+    }
 };
+static constexpr int kMaxProfIters = 64;
 
 extern "C" int vipe_ba_abi_version(void) { return 1; }
 extern "C" const char *vipe_ba_last_error(void) { return g_err.c_str(); }
@@ -272,11 +280,10 @@ static int check_tensors(const vipe_ba_plan *p, const vipe_ba_tensors *t, int mo
     return 0;
 }
 
-extern "C" int vipe_ba_linearize(const vipe_ba_plan *p, const vipe_ba_tensors *t, void *ws, int motion_only,
-                                 void *stream) {
+static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void *ws, int motion_only, cudaStream_t st,
+                          cudaEvent_t mid) {
     if (check_tensors(p, t, motion_only)) return 1;
     if (!ws) return fail("null workspace");
-    cudaStream_t st = (cudaStream_t)stream;
     unsigned char *w = (unsigned char *)ws;
     double *H = (double *)(w + p->off_sys);
     double *b = H + (size_t)p->npad * p->npad;
@@ -300,6 +307,7 @@ extern "C" int vipe_ba_linearize(const vipe_ba_plan *p, const vipe_ba_tensors *t
     la.qwbuf = (float *)(w + p->off_qw);
     VBA_CUDA(launch_linearize(la, nframes, std::max(p->dmax, 1), motion_only != 0, p->NT, p->PPT, st));
     p->launches++;
+    if (mid) VBA_CUDA(cudaEventRecord(mid, st));
 
     ReduceArgs ra;
     ra.tb = la.tb;
@@ -316,12 +324,16 @@ extern "C" int vipe_ba_linearize(const vipe_ba_plan *p, const vipe_ba_tensors *t
     return 0;
 }
 
-extern "C" int vipe_ba_solve_update(const vipe_ba_plan *p, const vipe_ba_tensors *t, void *ws, float lm, float ep,
-                                    int motion_only, void *stream) {
+extern "C" int vipe_ba_linearize(const vipe_ba_plan *p, const vipe_ba_tensors *t, void *ws, int motion_only,
+                                 void *stream) {
+    return linearize_impl(p, t, ws, motion_only, (cudaStream_t)stream, nullptr);
+}
+
+static int solve_update_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void *ws, float lm, float ep,
+                             int motion_only, cudaStream_t st, cudaEvent_t mid) {
     if (check_tensors(p, t, motion_only)) return 1;
     if (!ws) return fail("null workspace");
     if (p->P <= 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
     unsigned char *w = (unsigned char *)ws;
     double *H = (double *)(w + p->off_sys);
     double *b = H + (size_t)p->npad * p->npad;
@@ -329,6 +341,7 @@ extern "C" int vipe_ba_solve_update(const vipe_ba_plan *p, const vipe_ba_tensors
     int cnt = 0;
     VBA_CUDA(launch_damped_solve(H, b, p->n, p->npad, lm, ep, t->dx_out, flag, st, &cnt));
     p->launches += cnt;
+    if (mid) VBA_CUDA(cudaEventRecord(mid, st));
     const int nframes = p->k_hi - p->k_lo;
     if (!motion_only && nframes > 0) {
         BackArgs ba;
@@ -349,14 +362,60 @@ extern "C" int vipe_ba_solve_update(const vipe_ba_plan *p, const vipe_ba_tensors
     return 0;
 }
 
+extern "C" int vipe_ba_solve_update(const vipe_ba_plan *p, const vipe_ba_tensors *t, void *ws, float lm, float ep,
+                                    int motion_only, void *stream) {
+    return solve_update_impl(p, t, ws, lm, ep, motion_only, (cudaStream_t)stream, nullptr);
+}
+
+static int run_iteration(const vipe_ba_plan *p, const vipe_ba_tensors *t, void *ws, float lm, float ep, int motion_only,
+                         cudaStream_t st, cudaEvent_t *ev) {
+    // the system clear is counted with the linearise stage
+    if (ev) VBA_CUDA(cudaEventRecord(ev[0], st));
+    if (linearize_impl(p, t, ws, motion_only, st, ev ? ev[1] : nullptr)) return 1;
+    if (ev) VBA_CUDA(cudaEventRecord(ev[2], st));
+    if (solve_update_impl(p, t, ws, lm, ep, motion_only, st, ev ? ev[3] : nullptr)) return 1;
+    if (ev) VBA_CUDA(cudaEventRecord(ev[4], st));
+    return 0;
+}
+
+extern "C" int vipe_ba_profile_enable(vipe_ba_plan *p, int on) {
+    if (!p) return fail("null plan");
+    p->profile = on != 0;
+    if (p->profile && p->events.empty()) {
+        p->events.resize(5 * kMaxProfIters);
+        for (auto &e : p->events) VBA_CUDA(cudaEventCreate(&e));
+    }
+    p->prof_iters = 0;
+    return 0;
+}
+
+extern "C" int vipe_ba_profile_read(const vipe_ba_plan *p, float ms_out[4], int *iters_out) {
+    if (!p || !ms_out) return fail("null argument");
+    for (int s = 0; s < 4; s++) ms_out[s] = 0.0f;
+    if (iters_out) *iters_out = p->prof_iters;
+    for (int it = 0; it < p->prof_iters; it++)
+        for (int s = 0; s < 4; s++) {
+            float ms = 0.0f;
+            VBA_CUDA(cudaEventElapsedTime(&ms, p->events[5 * it + s], p->events[5 * it + s + 1]));
+            ms_out[s] += ms;
+        }
+    return 0;
+}
+
+// the stages of one iteration, with optional event records between them
+static int run_iteration(const vipe_ba_plan *p, const vipe_ba_tensors *t, void *ws, float lm, float ep, int motion_only,
+                         cudaStream_t st, cudaEvent_t *ev);
+
 extern "C" int vipe_ba_run(const vipe_ba_plan *p, const vipe_ba_tensors *t, void *ws, int iterations, float lm,
                            float ep, int motion_only, void *stream) {
     if (!p) return fail("null plan");
     if (p->world != 1) return fail("vipe_ba_run needs a single-rank plan; use linearize/solve_update with an all-reduce");
     p->launches = 0;
+    p->prof_iters = 0;
     for (int it = 0; it < iterations; it++) {
-        if (vipe_ba_linearize(p, t, ws, motion_only, stream)) return 1;
-        if (vipe_ba_solve_update(p, t, ws, lm, ep, motion_only, stream)) return 1;
+        cudaEvent_t *ev = (p->profile && it < kMaxProfIters) ? &p->events[5 * it] : nullptr;
+        if (run_iteration(p, t, ws, lm, ep, motion_only, (cudaStream_t)stream, ev)) return 1;
+        if (ev) p->prof_iters = it + 1;
     }
     return 0;
 }

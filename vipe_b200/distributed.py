@@ -1,0 +1,88 @@
+"""Keyframe-sharded bundle adjustment over one node.
+
+One process per GPU.  Disparities couple only to the edges that leave their own frame
+(geom_kernels.cu:292 reads disps[ii]; C, w, E are grouped by `ii`, :1365-1373), so every rank eliminates the
+disparities of the source frames it owns locally and only the reduced camera system
+[H ; b] (fp64, 6P x 6P + 6P) is summed across ranks -- one `all_reduce` per Gauss-Newton iteration over
+NCCL / NVLink.  The damped Cholesky solve is replicated (every rank reduces the same buffer, so every rank
+computes the same dx), back-substitution and disparity retraction are local to the owner, and the owned
+disparity rows are exchanged once per call, not per iteration.
+
+`ba_sharded` has the signature of `slam_ext.ba` plus a process group.  The engine (what runs between the
+collectives) is pluggable so the orchestration is testable with `gloo` on CPU; the product engine is the CUDA one.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .ext import slam_ext
+from .plan import cached_plan
+
+
+class CudaShardEngine:
+    """Calls the C ABI's two phases on this rank's shard (include/vipe_ba.h: vipe_ba_linearize / vipe_ba_solve_update)."""
+
+    def __init__(self, plan, poses, disps, intrinsics, disps_sens, targets, weights, eta, motion_only):
+        dev = poses.device
+        self.plan, self.dev, self.motion_only = plan, dev, bool(motion_only)
+        HW = plan.ht * plan.wd
+        self.dx = torch.zeros(plan.P, 6, dtype=torch.float32, device=dev)
+        self.dz = torch.zeros(plan.K, HW, dtype=torch.float32, device=dev)
+        self.ws = plan.workspace(dev)
+        self.tens = slam_ext._tensors(poses, disps, intrinsics, disps_sens, targets, weights, eta, self.dx, self.dz,
+                                      self.motion_only)
+        self.system, self.npad = plan.system_view(self.ws)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def linearize(self) -> torch.Tensor:
+        _lib.check(_lib.lib().vipe_ba_linearize(self.plan.handle, C.byref(self.tens), self.ws.data_ptr(),
+                                                int(self.motion_only), self._stream()), "vipe_ba_linearize")
+        return self.system
+
+    def solve_update(self, lm: float, ep: float):
+        _lib.check(_lib.lib().vipe_ba_solve_update(self.plan.handle, C.byref(self.tens), self.ws.data_ptr(), float(lm),
+                                                   float(ep), int(self.motion_only), self._stream()),
+                   "vipe_ba_solve_update")
+
+
+def ba_sharded(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, t1, iterations, lm, ep,
+               motion_only, group=None, engine_cls=CudaShardEngine, exchange=True):
+    """`slam_ext.ba` sharded by source keyframe across the ranks of `group`.
+
+    Every rank passes the full tensors (poses are replicated; for targets/weights only the rows of owned edges are
+    read).  On return `poses` is identical on all ranks and, if `exchange`, so are `disps[kx]` and `dz`."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    t0, t1 = int(t0), int(t1)
+    N, ht, wd = disps.shape
+    plan = cached_plan(ii.detach().to("cpu", torch.int64).contiguous(), jj.detach().to("cpu", torch.int64).contiguous(),
+                       N, ht, wd, t0, t1, rank, world)
+    eng = engine_cls(plan, poses, disps, intrinsics, disps_sens, targets, weights, eta, motion_only)
+    for _ in range(int(iterations)):
+        system = eng.linearize()
+        if world > 1:
+            dist.all_reduce(system, op=dist.ReduceOp.SUM, group=group)
+        eng.solve_update(lm, ep)
+    if exchange and world > 1 and not motion_only:
+        exchange_owned_rows(plan, disps, eng.dz, group)
+    return [eng.dx, eng.dz]
+
+
+def exchange_owned_rows(plan, disps, dz, group=None):
+    """Make disps[kx] and dz identical on all ranks: every rank contributes the rows it owns."""
+    lo, hi = plan.owned_range()
+    kx = plan.kx.to(disps.device)
+    HW = plan.ht * plan.wd
+    buf = torch.zeros(2, plan.K, HW, dtype=disps.dtype, device=disps.device)
+    buf[0, lo:hi] = disps.view(-1, HW)[kx[lo:hi]]
+    buf[1, lo:hi] = dz[lo:hi]
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    disps.view(-1, HW)[kx] = buf[0]
+    dz.copy_(buf[1])

@@ -142,7 +142,9 @@ def make_edges(cfg: BAConfig, gen: torch.Generator):
 
 
 # ----------------------------------------------------------------------------- generator
-def make_problem(cfg: BAConfig | str, clip: int = 0, sensor_on_even_frames: bool = False) -> BAProblem:
+def make_problem(cfg: BAConfig | str, clip: int = 0, sensor_on_even_frames: bool = False, noise_px: float = 0.25,
+                 perturb: float = 1.0) -> BAProblem:
+    """`noise_px`: std of the target noise; `perturb`: scale of the initial pose/disparity perturbation (0 = start at GT)."""
     if isinstance(cfg, str):
         cfg = CONFIGS[cfg]
     gen = torch.Generator().manual_seed(BASE_SEED + cfg.cfg_id + 1000 * clip)
@@ -187,7 +189,7 @@ def make_problem(cfg: BAConfig | str, clip: int = 0, sensor_on_even_frames: bool
         z = Xj[..., 2].clamp_min(1e-3)
         targets[s:s + 256, 0] = (intr[0] * Xj[..., 0] / z + intr[2]).reshape(-1, ht, wd).float()
         targets[s:s + 256, 1] = (intr[1] * Xj[..., 1] / z + intr[3]).reshape(-1, ht, wd).float()
-    targets += 0.25 * randn(E, 2, ht, wd, dtype=torch.float32)
+    targets += noise_px * randn(E, 2, ht, wd, dtype=torch.float32)
 
     weights = torch.sigmoid(randn(E, 2, ht, wd, dtype=torch.float32))
     drop = torch.rand(E, 1, ht, wd, generator=gen) < 0.1
@@ -202,10 +204,10 @@ def make_problem(cfg: BAConfig | str, clip: int = 0, sensor_on_even_frames: bool
         disps_sens[0::2] = disps_gt[0::2].float()
 
     # initial state = perturbed ground truth
-    pt, pq = _compose_left(randn(N, 6) * 0.01, t, q)
+    pt, pq = _compose_left(randn(N, 6) * (0.01 * perturb), t, q)
     poses = torch.cat([pt, pq], dim=-1)
     poses[0] = poses_gt[0]
-    disps = (disps_gt * (1.0 + 0.05 * randn(N, ht, wd))).clamp_min(0.01)
+    disps = (disps_gt * (1.0 + (0.05 * perturb) * randn(N, ht, wd))).clamp_min(0.01)
 
     return BAProblem(cfg, poses.float().contiguous(), disps.float().contiguous(), intr.float(), disps_sens,
                      targets.contiguous(), weights.contiguous(), eta.contiguous(), ii, jj, t0, t1,

@@ -1,0 +1,62 @@
+"""Keyframe-sharded CUDA path over NCCL (needs >= 2 GPUs on the box; skipped otherwise): the sharded result must
+match the single-GPU result of the same operator to fp32 rounding."""
+
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, name, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from vipe_b200.distributed import ba_sharded
+    from vipe_b200.synthetic import make_problem
+
+    pr = make_problem(name)
+    a = pr.args(dev)
+    dx, dz = ba_sharded(*a)
+    torch.cuda.synchronize()
+    if rank == 0:
+        torch.save({"poses": a[0].cpu(), "disps": a[1].cpu(), "dx": dx.cpu(), "dz": dz.cpu()}, out)
+    chk = torch.cat([a[0].reshape(-1), a[1].reshape(-1)]).clone()
+    ref = chk.clone()
+    dist.broadcast(ref, src=0)
+    assert torch.equal(chk, ref), "ranks disagree on the final state"
+    dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("name", ["c2", "c3"])
+def test_sharded_matches_single_gpu(lib_built, tmp_path, name):
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = min(world, 4)
+    from vipe_b200.ext import slam_ext
+    from vipe_b200.synthetic import disp_error, make_problem, pose_errors
+
+    out = tmp_path / "r0.pt"
+    mp.spawn(_worker, args=(world, _free_port(), name, str(out)), nprocs=world, join=True)
+    got = torch.load(out)
+    pr = make_problem(name)
+    a = pr.args(torch.device("cuda:0"))
+    slam_ext.ba(*a)
+    torch.cuda.synchronize()
+    te, re_ = pose_errors(got["poses"], a[0], pr.t0, pr.t1)
+    kx = torch.unique(torch.cat([torch.arange(pr.t0, pr.t1), pr.ii]))
+    de = disp_error(got["disps"], a[1], kx)
+    assert te <= 1e-5 and re_ <= 1e-5 and de <= 1e-4, (te, re_, de)

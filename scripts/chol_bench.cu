@@ -1,0 +1,179 @@
+// Developer benchmark of the dense Cholesky solve (chol.cu) on a random SPD system, with per-tile phase stamps.
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -DVBA_CHOL_TRACE -Ivipe_b200/csrc scripts/chol_bench.cu -o scripts/chol_bench
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cmath>
+#include <algorithm>
+#include "../vipe_b200/csrc/chol.cu"
+
+using namespace vba;
+
+
+// ---- micro timing of the tile primitives (single CTA), cycles via clock64
+__global__ void __launch_bounds__(CT) micro_kernel(double *out, long long *clk) {
+    extern __shared__ __align__(16) double sm[];
+    double *As = sm, *Bs = sm + TB * LD, *col = Bs + TB * LD, *dinv = col + TB, *Ltd = dinv + TB;
+    __shared__ int sh_ok;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // SPD tile in As (row-major DL)
+    for (int idx = tid; idx < TB * TB; idx += CT) {
+        const int r = idx >> 6, c = idx & 63;
+        As[r * DL + c] = (r == c) ? 100.0 + r : 1.0 / (1 + abs(r - c));
+        Bs[r * DL + c] = 0.5 + 0.001 * idx;
+    }
+    if (tid == 0) sh_ok = 1;
+    __syncthreads();
+    long long t0 = clock64();
+    tile_potrf(As, dinv, col, Ltd, &sh_ok);
+    long long t1 = clock64();
+    // warp-level pieces alone
+    double a[32];
+    long long t2 = 0, t3 = 0, t4 = 0;
+    if (warp == 0) {
+        for (int c = 0; c < 32; c++) a[c] = (lane == c) ? 100.0 + c : 1.0 / (1 + abs(lane - c));
+        double inv;
+        long long tt[5];
+#pragma unroll 1
+        for (int rep = 0; rep < 4; rep++) {
+            for (int c = 0; c < 32; c++) a[c] = (lane == c) ? 100.0 + c + rep : 1.0 / (1 + abs(lane - c));
+            tt[rep] = clock64();
+            warp_potrf32(a, col, lane, inv);
+            tt[rep + 1] = clock64();
+            if (lane == 0) clk[8 + rep] = tt[rep + 1] - tt[rep];
+        }
+        t2 = tt[3];
+        t3 = tt[4];
+        warp_trsm32<34>(a, Ltd, dinv);
+        t4 = clock64();
+        out[lane] = a[lane & 31] + inv;
+    }
+    __syncthreads();
+    // transposed L for tile_trsm: reuse As as if it were Lt (values irrelevant for timing)
+    long long t5 = clock64();
+    tile_trsm(Bs, As, dinv);
+    long long t6 = clock64();
+    double acc[4][4];
+    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) acc[r][c] = r + c;
+    __syncthreads();
+    long long t7 = clock64();
+    tile_gemm_sub(acc, As, Bs);
+    __syncthreads();
+    long long t8 = clock64();
+    if (tid == 0) {
+        clk[0] = t1 - t0; clk[1] = t3 - t2; clk[2] = t4 - t3; clk[3] = t6 - t5; clk[4] = t8 - t7;
+    }
+    out[64 + tid] = acc[0][0] + acc[3][3] + Bs[tid];
+}
+
+int main(int argc, char **argv) {
+    if (argc > 1 && atoi(argv[1]) == 0) {
+        double *out; long long *clk, h[5];
+        cudaMalloc(&out, 4096 * 8); cudaMalloc(&clk, 256);
+        const size_t smb = (size_t)(2 * TB * LD + 2 * TB + 32 * 34 + TB * DL) * sizeof(double);
+        cudaFuncSetAttribute(micro_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+        for (int r = 0; r < 3; r++) {
+            micro_kernel<<<1, CT, smb>>>(out, clk);
+            cudaDeviceSynchronize();
+            long long h2[4];
+            cudaMemcpy(h, clk, 40, cudaMemcpyDeviceToHost);
+            cudaMemcpy(h2, clk + 8, 32, cudaMemcpyDeviceToHost);
+            printf("warp_potrf32 repeated in a loop: %lld %lld %lld %lld\n", h2[0], h2[1], h2[2], h2[3]);
+            printf("cycles: tile_potrf64 %lld | warp_potrf32 %lld | warp_trsm32 %lld | tile_trsm64 %lld | tile_gemm_sub %lld   (%s)\n", h[0], h[1], h[2], h[3], h[4], cudaGetErrorString(cudaGetLastError()));
+        }
+        return 0;
+    }
+    const int n = argc > 1 ? atoi(argv[1]) : 1794;
+    const int reps = argc > 2 ? atoi(argv[2]) : 5;
+    const int npad = std::max(64, (n + 63) / 64 * 64);
+    const int T = npad / 64;
+    // SPD: banded + random, diagonally dominant-ish
+    std::vector<double> A((size_t)npad * npad, 0.0), b(npad, 0.0);
+    srand(1);
+    for (int i = 0; i < n; i++) {
+        for (int j = 0; j <= i; j++) {
+            double v = ((rand() % 2001) - 1000) / 1000.0;
+            if (i - j > 72 && (rand() % 10)) v = 0;
+            A[(size_t)i * npad + j] = v;
+        }
+        A[(size_t)i * npad + i] = 200.0 + (rand() % 100);
+        b[i] = ((rand() % 2001) - 1000) / 1000.0;
+    }
+    for (int i = n; i < npad; i++) A[(size_t)i * npad + i] = 1.0;
+    double *dH, *dsys, *ddinv;
+    float *ddx;
+    int *dscr;
+    long long *dtrace;
+    const size_t sysn = (size_t)npad * npad + npad;
+    cudaMalloc(&dsys, sysn * 8);
+    cudaMalloc(&dH, sysn * 8);
+    cudaMalloc(&ddinv, npad * 8);
+    cudaMalloc(&ddx, npad * 4);
+    const size_t nscr = chol_scratch_ints(npad);
+    cudaMalloc(&dscr, nscr * 4);
+    cudaMemset(dscr, 0, nscr * 4);
+    const int total = T * (T + 1) / 2 + T;
+    cudaMalloc(&dtrace, (size_t)total * 8 * 8);
+    cudaMemset(dtrace, 0, (size_t)total * 8 * 8);
+    cudaMemcpyToSymbol(g_trace, &dtrace, sizeof(dtrace));
+    std::vector<double> sys(sysn);
+    std::copy(A.begin(), A.end(), sys.begin());
+    std::copy(b.begin(), b.end(), sys.begin() + (size_t)npad * npad);
+    cudaMemcpy(dsys, sys.data(), sysn * 8, cudaMemcpyHostToDevice);
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    float best = 1e9;
+    for (int r = 0; r < reps; r++) {
+        cudaMemcpy(dH, dsys, sysn * 8, cudaMemcpyDeviceToDevice);
+        cudaDeviceSynchronize();
+        int cnt = 0;
+        cudaEventRecord(e0);
+        cudaError_t err = launch_damped_solve(dH, dH + (size_t)npad * npad, n, npad, 0.0f, 0.0f, ddx, dscr, ddinv, r + 1, 0, &cnt);
+        cudaEventRecord(e1);
+        cudaDeviceSynchronize();
+        if (err != cudaSuccess || cudaGetLastError() != cudaSuccess) { printf("cuda error %s\n", cudaGetErrorString(err)); return 1; }
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        best = std::min(best, ms);
+        printf("rep %d: %.3f ms\n", r, ms);
+    }
+    // residual check
+    std::vector<float> x(npad);
+    cudaMemcpy(x.data(), ddx, n * 4, cudaMemcpyDeviceToHost);
+    double rmax = 0, bmax = 0;
+    for (int i = 0; i < n; i++) {
+        double s = 0;
+        for (int j = 0; j < n; j++) s += (j <= i ? A[(size_t)i * npad + j] : A[(size_t)j * npad + i]) * x[j];
+        rmax = std::max(rmax, std::fabs(s - b[i]));
+        bmax = std::max(bmax, std::fabs(b[i]));
+    }
+    printf("n=%d T=%d best %.3f ms  residual max %.3e (|b| max %.3e)\n", n, T, best, rmax, bmax);
+    // trace analysis of the last rep
+    std::vector<long long> tr((size_t)total * 8);
+    cudaMemcpy(tr.data(), dtrace, tr.size() * 8, cudaMemcpyDeviceToHost);
+    long long t0 = tr[0];
+    double sum[8] = {0};
+    int cntd = 0, cnto = 0;
+    double dsum[8] = {0}, osum[8] = {0};
+    int t = 0;
+    for (int j = 0; j < T; j++) {
+        for (int i = j; i <= T; i++, t++) {
+            if (i == T) continue;
+            long long *s = &tr[(size_t)t * 8];
+            if (i == j) {
+                cntd++;
+                dsum[0] += (s[1] - s[0]); dsum[1] += (s[2] - s[1]); dsum[2] += (s[4] - s[2]); dsum[3] += (s[5] - s[4]); dsum[4] += (s[6] - s[5]);
+                if (j < 6 || j == T - 1) printf("diag %2d: start %8.1f us  load %5.1f  kloop %6.1f (last step %5.1f)  potrf %5.1f  store %5.1f  publish %5.1f  end %8.1f\n", j, (s[0] - t0) / 1e3,
+                    (s[1] - s[0]) / 1e3, (s[2] - s[1]) / 1e3, j ? (s[2] - s[7]) / 1e3 : 0.0, (s[4] - s[2]) / 1e3, (s[5] - s[4]) / 1e3, (s[6] - s[5]) / 1e3, (s[6] - t0) / 1e3);
+            } else {
+                cnto++;
+                osum[0] += (s[1] - s[0]); osum[1] += (s[2] - s[1]); osum[2] += (s[3] - s[2]); osum[3] += (s[4] - s[3]); osum[4] += (s[5] - s[4]); osum[5] += (s[6] - s[5]);
+                if (i == j + 1 && (j < 6)) printf("sub  %2d: start %8.1f us  load %5.1f  kloop %6.1f  waitLjj+load %5.1f  trsm %5.1f  store %5.1f  publish %5.1f  end %8.1f\n", j, (s[0] - t0) / 1e3,
+                    (s[1] - s[0]) / 1e3, (s[2] - s[1]) / 1e3, (s[3] - s[2]) / 1e3, (s[4] - s[3]) / 1e3, (s[5] - s[4]) / 1e3, (s[6] - s[5]) / 1e3, (s[6] - t0) / 1e3);
+            }
+        }
+    }
+    (void)sum;
+    printf("diag tiles avg (us): load %.2f kloop %.2f potrf %.2f store %.2f publish %.2f\n", dsum[0] / cntd / 1e3, dsum[1] / cntd / 1e3, dsum[2] / cntd / 1e3, dsum[3] / cntd / 1e3, dsum[4] / cntd / 1e3);
+    if (cnto) printf("off  tiles avg (us): load %.2f kloop %.2f wait+loadLjj %.2f trsm %.2f store %.2f publish %.2f\n", osum[0] / cnto / 1e3, osum[1] / cnto / 1e3, osum[2] / cnto / 1e3, osum[3] / cnto / 1e3, osum[4] / cnto / 1e3, osum[5] / cnto / 1e3);
+    return 0;
+}

@@ -41,7 +41,8 @@ struct vipe_ba_plan {
     // workspace layout (byte offsets)
     size_t off_kx = 0, off_fptr = 0, off_fedge = 0, off_ejj = 0, off_gbase = 0, off_mbase = 0, idx_bytes = 0;
     size_t off_epart = 0, off_gpart = 0, off_msc = 0, off_q = 0, off_qw = 0, off_sys = 0, off_dx = 0, off_flag = 0;
-    size_t total = 0;
+    size_t total = 0, flag_bytes = 0;
+    mutable int epoch = 0;
     std::vector<unsigned char> blob;  // host image of the index tables
     mutable int64_t launches = 0;
     // optional stage timing
@@ -188,8 +189,9 @@ extern "C" int vipe_ba_plan_create(const int64_t *ii, const int64_t *jj, int64_t
     p->off_q = take(sizeof(float) * (size_t)K * p->HW);
     p->off_qw = take(sizeof(float) * (size_t)K * p->HW);
     p->off_sys = take(sizeof(double) * ((size_t)p->npad * p->npad + p->npad));
-    p->off_dx = take(sizeof(float) * (size_t)p->npad);
-    p->off_flag = take(256);
+    p->off_dx = take(sizeof(double) * (size_t)p->npad);  // 1/diag(L) of the factorisation
+    p->off_flag = take(sizeof(int) * chol_scratch_ints(p->npad));
+    p->flag_bytes = sizeof(int) * chol_scratch_ints(p->npad);
     p->total = off;
 
     p->blob.assign(p->idx_bytes, 0);
@@ -237,6 +239,7 @@ extern "C" int64_t vipe_ba_launch_count(const vipe_ba_plan *p) { return p ? p->l
 extern "C" int vipe_ba_plan_upload(const vipe_ba_plan *p, void *ws, void *stream) {
     if (!p || !ws) return fail("null argument");
     VBA_CUDA(cudaMemcpyAsync(ws, p->blob.data(), p->idx_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    VBA_CUDA(cudaMemsetAsync((unsigned char *)ws + p->off_flag, 0, p->flag_bytes, (cudaStream_t)stream));
     return 0;
 }
 
@@ -337,9 +340,10 @@ static int solve_update_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, vo
     unsigned char *w = (unsigned char *)ws;
     double *H = (double *)(w + p->off_sys);
     double *b = H + (size_t)p->npad * p->npad;
-    int *flag = (int *)(w + p->off_flag);
+    int *scratch = (int *)(w + p->off_flag);
     int cnt = 0;
-    VBA_CUDA(launch_damped_solve(H, b, p->n, p->npad, lm, ep, t->dx_out, flag, st, &cnt));
+    p->epoch++;
+    VBA_CUDA(launch_damped_solve(H, b, p->n, p->npad, lm, ep, t->dx_out, scratch, (double *)(w + p->off_dx), p->epoch, st, &cnt));
     p->launches += cnt;
     if (mid) VBA_CUDA(cudaEventRecord(mid, st));
     const int nframes = p->k_hi - p->k_lo;

@@ -19,8 +19,11 @@ cudaError_t launch_pose_retr(float *poses, const float *dx, int t0, int t1, cuda
 //   H: [npad x npad] fp64 row-major, lower triangle valid on entry (destroyed);  b: [npad] fp64 (destroyed)
 //   diag += ep + lm*diag (geom_kernels.cu:1176); factor; solve; dx[n] fp32.  Failure => dx = 0 (:1186-1188).
 // Returns the number of kernels launched through *launches.
-cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx, int *flag,
-                                cudaStream_t st, int *launches);
+// `scratch` is chol_scratch_ints(npad) ints of device memory, zeroed once when the workspace is set up; `epoch` must be
+// a value never used before on this scratch (tile ready flags are epoch-valued so they need no per-solve reset).
+cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx, int *scratch,
+                                double *dinv /*[npad]*/, int epoch, cudaStream_t st, int *launches);
+size_t chol_scratch_ints(int npad);
 // zero [H ; b] and put the identity on the padded diagonal
 cudaError_t launch_system_clear(double *H, double *b, int n, int npad, cudaStream_t st);
 

@@ -2,16 +2,22 @@
 //
 // Replaces SparseBlock::solve (csrc/slam_ext/geom_kernels.cu:1172-1191): the reference copies the system to
 // the host and runs Eigen::SimplicialLLT<double>; here the factorisation never leaves the GPU.
-//   n <= kSmallMax : one CTA, matrix resident in shared memory (frontend windows, 6*P <= 160)
-//   otherwise      : right-looking blocked factorisation, 64-wide panels
-// A non-positive (or NaN) pivot raises *flag and the solve writes dx = 0, like the reference (:1186-1188).
+//
+// Tile dataflow (64x64 tiles, left-looking): persistent CTAs claim tiles in column-major order from an atomic
+// counter; tile (i,j) subtracts L_ik L_jk^T for k < j as soon as those tiles are published (per-tile ready flags,
+// release/acquire at gpu scope), then is factorised (i == j) or solved against L_jj (i > j) and published.
+// The right-hand side rides along as one extra tile row (forward substitution for free); a second dataflow
+// kernel does the backward substitution.  Claim order respects the dependencies, so every spin-wait is on a tile
+// that a resident CTA is already working on: no cooperative launch is needed.
+// A non-positive (or NaN) pivot raises *fail and the solve writes dx = 0, like the reference (:1186-1188).
 #include "ba_launch.h"
 
 namespace vba {
 
-constexpr int kSmallMax = 160;
-constexpr int NB = kCholBlock;  // 64
-constexpr int LDS = NB + 1;
+constexpr int TB = kCholBlock;  // 64
+constexpr int LD = TB + 2;      // 66: keeps 16-byte alignment of 4-double groups in the [k][row] layout
+constexpr int CT = 256;         // threads per CTA
+constexpr int DL = TB + 1;      // row stride of row-major tiles in shared memory (conflict-free column access)
 
 // ------------------------------------------------------------------------------------------------
 __global__ void pad_identity_kernel(double *H, int n, int npad) {
@@ -32,302 +38,532 @@ cudaError_t launch_system_clear(double *H, double *b, int n, int npad, cudaStrea
 }
 
 // ------------------------------------------------------------------------------------------------
-// factor an m x m lower-triangular block held in shared memory (row stride lds); returns false on failure.
-// All threads of the CTA must call it.
-__device__ bool smem_potrf(double *A, int m, int lds) {
-    const int tid = threadIdx.x, NT = blockDim.x;
-    for (int j = 0; j < m; j++) {
-        const double ajj = A[j * lds + j];
-        if (!(ajj > 0.0)) return false;  // uniform: every thread reads the same value
-        const double dj = sqrt(ajj);
-        const double inv = 1.0 / dj;
-        __syncthreads();
-        for (int i = j + 1 + tid; i < m; i += NT) A[i * lds + j] *= inv;
-        if (tid == 0) A[j * lds + j] = dj;
-        __syncthreads();
-        const int r = m - j - 1;
-        for (int idx = tid; idx < r * r; idx += NT) {
-            const int a = idx / r, c = idx - a * r;
-            if (c <= a) {
-                const int i = j + 1 + a, k = j + 1 + c;
-                A[i * lds + k] -= A[i * lds + j] * A[k * lds + j];
-            }
-        }
-        __syncthreads();
-    }
-    return true;
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
-
-__global__ void __launch_bounds__(512) chol_small_kernel(const double *__restrict__ H, const double *__restrict__ b,
-                                                        int n, int ld, float lm, float ep, float *__restrict__ dx,
-                                                        int *flag) {
-    extern __shared__ __align__(16) double sm[];
-    const int lds = n | 1;
-    double *A = sm;
-    double *bs = A + (size_t)n * lds;
-    const int tid = threadIdx.x, NT = blockDim.x;
-    for (int idx = tid; idx < n * n; idx += NT) {
-        const int i = idx / n, j = idx - i * n;
-        if (j <= i) {
-            double v = H[(size_t)i * ld + j];
-            if (i == j) v += (double)ep + (double)lm * v;  // geom_kernels.cu:1176
-            A[i * lds + j] = v;
-        }
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// all threads call; returns after flag == epoch is visible to the whole CTA
+__device__ __forceinline__ void wait_flag(const int *f, int epoch) {
+    if (threadIdx.x == 0) {
+        while (ld_acquire(f) != epoch) __nanosleep(32);
     }
-    for (int i = tid; i < n; i += NT) bs[i] = b[i];
     __syncthreads();
-    const bool ok = smem_potrf(A, n, lds);
-    if (!ok) {
-        for (int i = tid; i < n; i += NT) dx[i] = 0.0f;
-        if (tid == 0) *flag = 1;
-        return;
-    }
-    // forward substitution (column oriented)
-    for (int j = 0; j < n; j++) {
-        const double yj = bs[j] / A[j * lds + j];
-        __syncthreads();
-        if (tid == 0) bs[j] = yj;
-        for (int i = j + 1 + tid; i < n; i += NT) bs[i] -= A[i * lds + j] * yj;
-        __syncthreads();
-    }
-    // backward substitution with L^T
-    for (int j = n - 1; j >= 0; j--) {
-        const double xj = bs[j] / A[j * lds + j];
-        __syncthreads();
-        if (tid == 0) bs[j] = xj;
-        for (int i = tid; i < j; i += NT) bs[i] -= A[j * lds + i] * xj;
-        __syncthreads();
-    }
-    for (int i = tid; i < n; i += NT) dx[i] = (float)bs[i];
-    if (tid == 0) *flag = 0;
 }
-
-// ------------------------------------------------------------------------------------------------
-// blocked path
-__global__ void chol_damp_kernel(double *H, int n, int ld, float lm, float ep, int *flag) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) *flag = 0;
-    if (i < n) {
-        const double v = H[(size_t)i * ld + i];
-        H[(size_t)i * ld + i] = v + (double)ep + (double)lm * v;
+// all threads call after their global writes
+__device__ __forceinline__ void publish_flag(int *f, int epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        st_release(f, epoch);
     }
 }
 
-// CTA 0 factors the diagonal block and writes it back; CTA c >= 1 re-factors it locally (identical
-// arithmetic) and solves its 64-row slab of the panel: X = A_rk L_kk^-T.
-__global__ void __launch_bounds__(256) chol_panel_kernel(double *H, int ld, int k0, int *flag) {
-    extern __shared__ __align__(16) double dyn_sm[];
-    double *D = dyn_sm;
-    double *X = dyn_sm + NB * LDS;
-    if (*flag) return;
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int r = idx / NB, c = idx - r * NB;
-        D[r * LDS + c] = (c <= r) ? H[(size_t)(k0 + r) * ld + k0 + c] : 0.0;
-    }
-    const int r0 = k0 + blockIdx.x * NB;
-    if (blockIdx.x > 0) {
-        for (int idx = tid; idx < NB * NB; idx += 256) {
-            const int r = idx / NB, c = idx - r * NB;
-            X[r * LDS + c] = H[(size_t)(r0 + r) * ld + k0 + c];
-        }
-    }
-    __syncthreads();
-    const bool ok = smem_potrf(D, NB, LDS);
-    if (!ok) {
-        if (blockIdx.x == 0 && tid == 0) *flag = 1;
-        return;
-    }
-    if (blockIdx.x == 0) {
-        for (int idx = tid; idx < NB * NB; idx += 256) {
-            const int r = idx / NB, c = idx - r * NB;
-            if (c <= r) H[(size_t)(k0 + r) * ld + k0 + c] = D[r * LDS + c];
-        }
-        return;
-    }
-    // 4 threads per row: thread (row, part) accumulates the terms p = part, part+4, ... of the dot product
-    const int row = tid >> 2, part = tid & 3;
-    double *xr = X + row * LDS;
-    for (int c = 0; c < NB; c++) {
-        const double *dc = D + c * LDS;
-        double s = 0.0;
-        for (int p = part; p < c; p += 4) s += xr[p] * dc[p];
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        const double v = (xr[c] - s) / dc[c];
-        __syncwarp();
-        if (part == 0) xr[c] = v;
-        __syncwarp();
-    }
-    __syncthreads();
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int r = idx / NB, c = idx - r * NB;
-        H[(size_t)(r0 + r) * ld + k0 + c] = X[r * LDS + c];
-    }
+#ifdef VBA_CHOL_TRACE
+__device__ long long *g_trace = nullptr;  // [tile][8] globaltimer stamps (developer builds only)
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
+#define TRACE(tile, slot)                                                          \
+    do {                                                                           \
+        if (threadIdx.x == 0 && g_trace) g_trace[(size_t)(tile) * 8 + (slot)] = gtime(); \
+    } while (0)
+#else
+#define TRACE(tile, slot) \
+    do {                  \
+    } while (0)
+#endif
 
-// trailing update: for every lower tile (bi >= bj > kb): A_ij -= L_ik L_jk^T   (64x64x64, fp64 FMA)
-__global__ void __launch_bounds__(256) chol_update_kernel(double *H, int ld, int k0, int nb_rem, const int *flag) {
-    extern __shared__ __align__(16) double dyn_sm[];
-    double *As = dyn_sm;             // [k][i]
-    double *Bs = dyn_sm + NB * LDS;  // [k][j]
-    if (*flag) return;
-    // decode tile index -> (ti >= tj) within the remaining nb_rem x nb_rem block grid
-    const int t = blockIdx.x;
-    int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-    while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
-    while (ti * (ti + 1) / 2 > t) ti--;
-    const int tj = t - ti * (ti + 1) / 2;
-    const int i0 = k0 + NB + ti * NB, j0 = k0 + NB + tj * NB;
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int r = idx / NB, c = idx - r * NB;  // r: row within tile, c: k index (contiguous in memory)
-        As[c * LDS + r] = H[(size_t)(i0 + r) * ld + k0 + c];
-        Bs[c * LDS + r] = H[(size_t)(j0 + r) * ld + k0 + c];
-    }
-    __syncthreads();
-    const int ty = tid >> 4, tx = tid & 15;
-    double acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+struct CholArgs {
+    double *H;   // [npad x npad] row-major, lower triangle valid; overwritten by L
+    double *b;   // [npad]; overwritten by y = L^-1 b, then by x
+    int ld, T, n;
+    float lm, ep;
+    int *flags;    // [(T+1) x T] tile ready flags, value == epoch when ready; row T is the rhs row
+    int *xflags;   // [T] ready flags of the backward substitution
+    int *counter;  // [2] tile counters (factorisation, backward), zero on entry
+    int *fail;     // zero on entry
+    int epoch;
+    float *dx;
+    double *dinv;  // [npad] 1 / diag(L)
+};
+
+// thread (tx, ty) owns rows ty*4..+3 and columns tx*4..+3 of a 64x64 tile; tx = tid / 16 so that the 16 owners of
+// a column group share a warp (pivot broadcast by shuffle)
+#define TX (threadIdx.x >> 4)
+#define TY (threadIdx.x & 15)
+
+// acc -= A * B^T with As/Bs in [k][row] layout (row stride LD); thread (TX, TY) owns a 4x4 register tile.
+// Measured on B200: an fp64 outer-product loop fed from shared memory sustains ~26-28 DFMA/clk/SM whether the
+// register tile is 4x4 or 8x8 (45-48 from registers alone, 62 peak), so the small tile wins on registers.
+__device__ __forceinline__ void tile_gemm_sub(double (&acc)[4][4], const double *As, const double *Bs) {
+    const int r0 = TY * 4, c0 = TX * 4;
 #pragma unroll 8
-    for (int k = 0; k < NB; k++) {
-        double av[4], bv[4];
-#pragma unroll
-        for (int a = 0; a < 4; a++) av[a] = As[k * LDS + ty * 4 + a];
-#pragma unroll
-        for (int b = 0; b < 4; b++) bv[b] = Bs[k * LDS + tx * 4 + b];
+    for (int k = 0; k < TB; k++) {
+        const double2 a01 = *reinterpret_cast<const double2 *>(As + k * LD + r0);
+        const double2 a23 = *reinterpret_cast<const double2 *>(As + k * LD + r0 + 2);
+        const double2 b01 = *reinterpret_cast<const double2 *>(Bs + k * LD + c0);
+        const double2 b23 = *reinterpret_cast<const double2 *>(Bs + k * LD + c0 + 2);
+        const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+        const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int b = 0; b < 4; b++) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
-    }
-#pragma unroll
-    for (int a = 0; a < 4; a++) {
-        double *row = H + (size_t)(i0 + ty * 4 + a) * ld + j0 + tx * 4;
-#pragma unroll
-        for (int b = 0; b < 4; b++) row[b] -= acc[a][b];
+            for (int b = 0; b < 4; b++) acc[a][b] = fma(-av[a], bv[b], acc[a][b]);
     }
 }
 
-// forward + backward substitution on the factor, one CTA, rhs resident in shared memory
-__global__ void __launch_bounds__(1024) chol_solve_kernel(const double *__restrict__ L, const double *__restrict__ b,
-                                                         int n, int npad, float *__restrict__ dx, const int *flag) {
-    extern __shared__ __align__(16) double sm[];
-    double *bs = sm;          // [npad]
-    double *D = bs + npad;    // [NB][LDS]
-    double *ys = D + NB * LDS;  // [NB]
-    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    if (*flag) {
-        for (int i = tid; i < n; i += NT) dx[i] = 0.0f;
-        return;
+// register tile (acc) -> row-major shared tile S[64][DL]
+__device__ __forceinline__ void acc_to_smem(const double (&acc)[4][4], double *S) {
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) S[(TY * 4 + r) * DL + TX * 4 + c] = acc[r][c];
+}
+
+// load a 64x64 tile (global row-major, leading dim ld) into shared memory transposed: S[k][row].
+// All 8 loads of a thread are issued before the first store so that one L2 round trip covers the tile.
+__device__ __forceinline__ void load_tile_T(double *S, const double *__restrict__ G, int ld) {
+    double2 v[TB * TB / 2 / CT];
+#pragma unroll
+    for (int u = 0; u < TB * TB / 2 / CT; u++) {
+        const int idx = threadIdx.x + u * CT;
+        const int r = idx >> 5, k2 = (idx & 31) * 2;
+        v[u] = __ldcg(reinterpret_cast<const double2 *>(G + (size_t)r * ld + k2));
     }
-    for (int i = tid; i < npad; i += NT) bs[i] = b[i];
-    const int nblk = npad / NB;
-    for (int kb = 0; kb < nblk; kb++) {
-        const int k0 = kb * NB;
-        __syncthreads();
-        for (int idx = tid; idx < NB * NB; idx += NT) {
-            const int r = idx / NB, c = idx - r * NB;
-            D[r * LDS + c] = L[(size_t)(k0 + r) * npad + k0 + c];
+#pragma unroll
+    for (int u = 0; u < TB * TB / 2 / CT; u++) {
+        const int idx = threadIdx.x + u * CT;
+        const int r = idx >> 5, k2 = (idx & 31) * 2;
+        S[k2 * LD + r] = v[u].x;
+        S[(k2 + 1) * LD + r] = v[u].y;
+    }
+}
+
+// 1/sqrt(x) in fp64: MUFU.RSQ64H seed (rsqrt.approx.ftz.f64, ~2^-22) and one third-order correction
+//   e = 1 - x y^2,  y <- y + y e (1/2 + 3/8 e)          (error O(e^3) ~ 2^-66)
+// Branch-free: it sits on the critical path of every Cholesky pivot.  Valid for normal positive x.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x * y, y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    return fma(y * e, p, y);
+}
+
+
+// Warp-level Cholesky of a 32x32 block: lane r holds row r in registers.  On exit a[c] = L[r][c] (0 above the
+// diagonal).  colbuf: 32 doubles of shared memory private to the warp.  No block-wide barriers.
+__device__ __forceinline__ bool warp_potrf32(double (&a)[32], double *colbuf, int lane, double &my_inv) {
+    bool ok = true;
+    my_inv = 0.0;
+    // every lane tracks its own diagonal entry so that the next pivot does not wait for the column exchange
+    double diag = 0.0;
+#pragma unroll
+    for (int c = 0; c < 32; c++)
+        if (lane == c) diag = a[c];
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const double piv = __shfl_sync(0xffffffffu, diag, j);
+        const bool good = (piv > 1e-290) && (piv < 1e290);  // also false for NaN
+        ok = ok && good;
+        const double inv = good ? fast_rsqrt(piv) : 0.0;
+        if (lane == j) my_inv = inv;
+        double l = ((lane == j) ? piv : a[j]) * inv;  // lane j: piv * inv = sqrt(piv)
+        if (lane < j) l = 0.0;
+        a[j] = l;
+        diag = fma(-l, l, diag);  // lanes > j: a_rr -= l_rj^2  (lane j's diag is not used again)
+        double *cb = colbuf + (j & 1) * 32;
+        cb[lane] = l;
+        __syncwarp();
+#pragma unroll
+        for (int k = j + 1; k < 32; k++) a[k] = fma(-l, cb[k], a[k]);
+    }
+    __syncwarp();
+    return ok;
+}
+
+// Warp-level X = A L^-T for a 32x32 block: lane r holds row r of A in registers; L (lower) is read from shared
+// memory TRANSPOSED, Lt[c * ldt + q] = L[q][c] (so that vectorised broadcast loads pair up independent updates),
+// dinv[c] = 1 / L[c][c].
+template <int LDT>
+__device__ __forceinline__ void warp_trsm32(double (&a)[32], const double *Lt, const double *dinv) {
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+        const double x = a[c] * dinv[c];
+        a[c] = x;
+#pragma unroll
+        for (int q = c + 1; q < 32; q++) a[q] = fma(-x, Lt[c * LDT + q], a[q]);
+    }
+}
+
+// D[64][DL] (row-major, shared): factorise the lower triangle in place, write 1/diag to dinv[64].
+// 2x2 blocking: potrf32 (warp 0) -> trsm32 (warp 1) -> syrk (all) -> potrf32 (warp 0).  All threads must call.
+__device__ bool tile_potrf(double *D, double *dinv, double *colbuf, double *Lt, int *sh_ok) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double a[32];
+    if (warp == 0) {
+#pragma unroll
+        for (int c = 0; c < 32; c++) a[c] = D[lane * DL + c];
+        double my_inv;
+        const bool ok = warp_potrf32(a, colbuf, lane, my_inv);
+#pragma unroll
+        for (int c = 0; c < 32; c++) {
+            D[lane * DL + c] = a[c];
+            Lt[c * 34 + lane] = a[c];
+        }
+        dinv[lane] = my_inv;
+        if (!ok && lane == 0) *sh_ok = 0;
+    }
+    __syncthreads();
+    if (warp == 1) {
+#pragma unroll
+        for (int c = 0; c < 32; c++) a[c] = D[(32 + lane) * DL + c];
+        warp_trsm32<34>(a, Lt, dinv);
+#pragma unroll
+        for (int c = 0; c < 32; c++) D[(32 + lane) * DL + c] = a[c];
+    }
+    __syncthreads();
+    {   // A22 -= L21 L21^T : thread -> 2x2 outputs
+        const int r0 = 32 + (tid >> 4) * 2, c0 = 32 + (tid & 15) * 2;
+        double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+#pragma unroll 8
+        for (int k = 0; k < 32; k++) {
+            const double x0 = D[r0 * DL + k], x1 = D[(r0 + 1) * DL + k];
+            const double y0 = D[c0 * DL + k], y1 = D[(c0 + 1) * DL + k];
+            s00 = fma(x0, y0, s00), s01 = fma(x0, y1, s01), s10 = fma(x1, y0, s10), s11 = fma(x1, y1, s11);
         }
         __syncthreads();
-        if (warp == 0) {
-            for (int c = 0; c < NB; c++) {
-                const double yc = bs[k0 + c] / D[c * LDS + c];
-                __syncwarp();
-                for (int r = lane; r < NB; r += 32) {
-                    if (r > c) bs[k0 + r] -= D[r * LDS + c] * yc;
-                    if (r == c) {
-                        bs[k0 + r] = yc;
-                        ys[c] = yc;
-                    }
-                }
-                __syncwarp();
+        D[r0 * DL + c0] -= s00, D[r0 * DL + c0 + 1] -= s01, D[(r0 + 1) * DL + c0] -= s10, D[(r0 + 1) * DL + c0 + 1] -= s11;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int c = 0; c < 32; c++) a[c] = D[(32 + lane) * DL + 32 + c];
+        double my_inv;
+        const bool ok = warp_potrf32(a, colbuf, lane, my_inv);
+#pragma unroll
+        for (int c = 0; c < 32; c++) D[(32 + lane) * DL + 32 + c] = a[c];
+        dinv[32 + lane] = my_inv;
+        if (!ok && lane == 0) *sh_ok = 0;
+    }
+    __syncthreads();
+    return *sh_ok != 0;
+}
+
+// X[64][DL] (row-major, shared) <- X L^-T; L is given transposed, Lt[c * LD + q] = L[q][c] (load_tile_T layout),
+// dinv[64] = 1 / diag(L).  All threads must call.
+__device__ void tile_trsm(double *X, const double *Lt, const double *dinv) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double a[32];
+    if (warp < 2) {  // X1 = A1 L11^-T, one row per lane
+        const int r = warp * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < 32; c++) a[c] = X[r * DL + c];
+        warp_trsm32<LD>(a, Lt, dinv);
+#pragma unroll
+        for (int c = 0; c < 32; c++) X[r * DL + c] = a[c];
+    }
+    __syncthreads();
+    {   // A2 -= X1 L21^T : 64x32 outputs, K = 32; thread -> 2 rows x 4 cols
+        const int r0 = (tid >> 3) * 2, c0 = 32 + (tid & 7) * 4;
+        double s[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+#pragma unroll 8
+        for (int k = 0; k < 32; k++) {
+            const double x0 = X[r0 * DL + k], x1 = X[(r0 + 1) * DL + k];
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const double l = Lt[k * LD + c0 + b];
+                s[0][b] = fma(x0, l, s[0][b]);
+                s[1][b] = fma(x1, l, s[1][b]);
             }
         }
-        __syncthreads();
-        for (int i = k0 + NB + tid; i < npad; i += NT) {
-            const double *row = L + (size_t)i * npad + k0;
-            double s = 0.0;
-#pragma unroll 8
-            for (int c = 0; c < NB; c++) s += row[c] * ys[c];
-            bs[i] -= s;
-        }
-    }
-    for (int kb = nblk - 1; kb >= 0; kb--) {
-        const int k0 = kb * NB;
-        __syncthreads();
-        for (int idx = tid; idx < NB * NB; idx += NT) {
-            const int r = idx / NB, c = idx - r * NB;
-            D[r * LDS + c] = L[(size_t)(k0 + r) * npad + k0 + c];
-        }
-        __syncthreads();
-        if (warp == 0) {
-            for (int c = NB - 1; c >= 0; c--) {
-                const double xc = bs[k0 + c] / D[c * LDS + c];
-                __syncwarp();
-                for (int r = lane; r < NB; r += 32) {
-                    if (r < c) bs[k0 + r] -= D[c * LDS + r] * xc;
-                    if (r == c) {
-                        bs[k0 + r] = xc;
-                        ys[c] = xc;
-                    }
-                }
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-        for (int i = tid; i < k0; i += NT) {
-            double s = 0.0;
-#pragma unroll 8
-            for (int c = 0; c < NB; c++) s += L[(size_t)(k0 + c) * npad + i] * ys[c];
-            bs[i] -= s;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            X[r0 * DL + c0 + b] -= s[0][b];
+            X[(r0 + 1) * DL + c0 + b] -= s[1][b];
         }
     }
     __syncthreads();
-    for (int i = tid; i < n; i += NT) dx[i] = (float)bs[i];
+    if (warp < 2) {  // X2 = A2 L22^-T
+        const int r = warp * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < 32; c++) a[c] = X[r * DL + 32 + c];
+        warp_trsm32<LD>(a, Lt + 32 * LD + 32, dinv + 32);
+#pragma unroll
+        for (int c = 0; c < 32; c++) X[r * DL + 32 + c] = a[c];
+    }
+    __syncthreads();
 }
 
-cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx, int *flag,
-                                cudaStream_t st, int *launches) {
-    cudaError_t err;
-    int cnt = 0;
-    if (n <= kSmallMax) {
-        const size_t sm = ((size_t)n * (n | 1) + n) * sizeof(double);
-        err = cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        if (err != cudaSuccess) return err;
-        chol_small_kernel<<<1, 512, sm, st>>>(H, b, n, npad, lm, ep, dx, flag);
-        cnt++;
-    } else {
-        chol_damp_kernel<<<(n + 255) / 256, 256, 0, st>>>(H, n, npad, lm, ep, flag);
-        cnt++;
-        const int nblk = npad / NB;
-        const size_t sm2 = 2 * NB * LDS * sizeof(double);
-        err = cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-        if (err != cudaSuccess) return err;
-        err = cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-        if (err != cudaSuccess) return err;
-        for (int kb = 0; kb < nblk; kb++) {
-            const int k0 = kb * NB;
-            const int rem = nblk - kb - 1;
-            chol_panel_kernel<<<1 + rem, 256, sm2, st>>>(H, npad, k0, flag);
-            cnt++;
-            if (rem > 0) {
-                chol_update_kernel<<<rem * (rem + 1) / 2, 256, sm2, st>>>(H, npad, k0, rem, flag);
-                cnt++;
+__global__ void __launch_bounds__(CT, 2) chol_factor_kernel(const CholArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    double *As = sm;             // [64][LD]
+    double *Bs = sm + TB * LD;   // [64][LD]
+    double *col = Bs + TB * LD;  // [64]
+    double *dinv = col + TB;     // [64]
+    double *Ltd = dinv + TB;     // [32][34] transposed L11 of the diagonal tile
+    double *Ct = Ltd + 32 * 34;  // [64][DL] the tile being computed
+    __shared__ int sh_tile, sh_ok;
+    const int T = a.T, ld = a.ld, tid = threadIdx.x;
+    const int total = T * (T + 1) / 2 + T;  // lower tiles + one rhs tile per column
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            sh_tile = atomicAdd(a.counter, 1);
+            sh_ok = 1;
+        }
+        __syncthreads();
+        const int t = sh_tile;
+        if (t >= total) return;
+        // column j holds T - j + 1 tiles (rows j..T, row T = rhs); start(j) = j*(T+1) - j*(j-1)/2
+        int j = 0;
+        {
+            int lo = 0, hi = T - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (mid * (T + 1) - mid * (mid - 1) / 2 <= t) lo = mid;
+                else hi = mid - 1;
+            }
+            j = lo;
+        }
+        const int i = j + (t - (j * (T + 1) - j * (j - 1) / 2));
+        const int j0 = j * TB;
+        TRACE(t, 0);
+
+        if (i == T) {
+            // ---- right-hand side tile: y_j = L_jj^-1 (b_j - sum_k L_jk y_k)
+            double part = 0.0;
+            const int c = tid & 63, q = tid >> 6;  // 4 threads per entry, each takes 16 of the 64 k's
+            for (int k = 0; k < j; k++) {
+                wait_flag(a.flags + (size_t)T * T + k, a.epoch);
+                wait_flag(a.flags + (size_t)j * T + k, a.epoch);
+                const double *Lrow = a.H + (size_t)(j0 + c) * ld + k * TB + q * 16;
+                const double *yk = a.b + k * TB + q * 16;
+#pragma unroll
+                for (int p = 0; p < 16; p += 2) {
+                    const double2 l = __ldcg(reinterpret_cast<const double2 *>(Lrow + p));
+                    const double2 y = __ldcg(reinterpret_cast<const double2 *>(yk + p));
+                    part = fma(l.x, y.x, fma(l.y, y.y, part));
+                }
+            }
+            As[q * TB + c] = part;
+            wait_flag(a.flags + (size_t)j * T + j, a.epoch);
+            load_tile_T(Bs, a.H + (size_t)j0 * ld + j0, ld);  // Bs[k][r] = L_jj[r][k]
+            if (tid < TB) dinv[tid] = __ldcg(a.dinv + j0 + tid);
+            __syncthreads();
+            if (tid < 32) {
+                // forward substitution by one warp: lane owns entries lane and lane+32
+                double v0 = __ldcg(a.b + j0 + tid) - (As[tid] + As[TB + tid] + As[2 * TB + tid] + As[3 * TB + tid]);
+                double v1 = __ldcg(a.b + j0 + 32 + tid) - (As[32 + tid] + As[TB + 32 + tid] + As[2 * TB + 32 + tid] + As[3 * TB + 32 + tid]);
+                for (int c2 = 0; c2 < TB; c2++) {
+                    const double src = (c2 < 32) ? v0 : v1;
+                    const double yc = __shfl_sync(0xffffffffu, src, c2 & 31) * dinv[c2];
+                    if (tid == (c2 & 31)) {
+                        if (c2 < 32) v0 = yc; else v1 = yc;
+                    }
+                    // Bs[c2][r] = L[r][c2]
+                    if (tid > c2) v0 = fma(-Bs[c2 * LD + tid], yc, v0);
+                    if (tid + 32 > c2) v1 = fma(-Bs[c2 * LD + tid + 32], yc, v1);
+                    if (tid == (c2 & 31)) {  // keep the solved entry
+                        if (c2 < 32) v0 = yc; else v1 = yc;
+                    }
+                }
+                a.b[j0 + tid] = v0;
+                a.b[j0 + 32 + tid] = v1;
+            }
+            publish_flag(a.flags + (size_t)T * T + j, a.epoch);
+            continue;
+        }
+
+        const int i0 = i * TB;
+        // ---- load A_ij into registers (damping on the diagonal of diagonal tiles: geom_kernels.cu:1176)
+        const int tx = TX, ty = TY;
+        double acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const double *src = a.H + (size_t)(i0 + ty * 4 + r) * ld + j0 + tx * 4;
+            const double2 v01 = __ldcg(reinterpret_cast<const double2 *>(src));
+            const double2 v23 = __ldcg(reinterpret_cast<const double2 *>(src + 2));
+            acc[r][0] = v01.x, acc[r][1] = v01.y, acc[r][2] = v23.x, acc[r][3] = v23.y;
+        }
+        if (i == j && tx == ty) {
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int g = i0 + ty * 4 + r;
+                if (g < a.n) acc[r][r] += (double)a.ep + (double)a.lm * acc[r][r];
             }
         }
-        const size_t sm = ((size_t)npad + NB * LDS + NB) * sizeof(double);
-        err = cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        if (err != cudaSuccess) return err;
-        chol_solve_kernel<<<1, 1024, sm, st>>>(H, b, n, npad, dx, flag);
-        cnt++;
+        TRACE(t, 1);
+        // ---- left-looking updates
+        for (int k = 0; k < j; k++) {
+            wait_flag(a.flags + (size_t)i * T + k, a.epoch);
+            if (i != j) wait_flag(a.flags + (size_t)j * T + k, a.epoch);
+            TRACE(t, 7);
+            load_tile_T(As, a.H + (size_t)i0 * ld + k * TB, ld);
+            if (i != j) load_tile_T(Bs, a.H + (size_t)j0 * ld + k * TB, ld);
+            __syncthreads();
+            tile_gemm_sub(acc, As, (i != j) ? Bs : As);
+            __syncthreads();
+        }
+        acc_to_smem(acc, Ct);
+        __syncthreads();
+        TRACE(t, 2);
+        if (i == j) {
+            const bool ok = tile_potrf(Ct, dinv, col, Ltd, &sh_ok);
+            TRACE(t, 4);
+            if (!ok && tid == 0) *a.fail = 1;
+            // store L_jj (zero above the diagonal) and 1/diag
+            for (int idx = tid; idx < TB * TB; idx += CT) {
+                const int r = idx >> 6, c = idx & 63;
+                a.H[(size_t)(i0 + r) * ld + j0 + c] = (c <= r) ? Ct[r * DL + c] : 0.0;
+            }
+            if (tid < TB) a.dinv[j0 + tid] = dinv[tid];
+        } else {
+            wait_flag(a.flags + (size_t)j * T + j, a.epoch);
+            load_tile_T(As, a.H + (size_t)j0 * ld + j0, ld);  // As[c][q] = L_jj[q][c]
+            if (tid < TB) dinv[tid] = __ldcg(a.dinv + j0 + tid);
+            __syncthreads();
+            TRACE(t, 3);
+            tile_trsm(Ct, As, dinv);
+            TRACE(t, 4);
+            for (int idx = tid; idx < TB * TB; idx += CT) {
+                const int r = idx >> 6, c = idx & 63;
+                a.H[(size_t)(i0 + r) * ld + j0 + c] = Ct[r * DL + c];
+            }
+        }
+        TRACE(t, 5);
+        publish_flag(a.flags + (size_t)i * T + j, a.epoch);
+        TRACE(t, 6);
     }
-    if (launches) *launches += cnt;
+}
+
+// backward substitution x = L^-T y, one CTA per column block (claimed in descending order).
+// The diagonal tile and 1/diag are staged before the first wait so that only the x_i chain is exposed.
+__global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
+    extern __shared__ __align__(16) double bsm[];
+    double *Ld = bsm;                    // [64][65] L_jj
+    double *Ls = Ld + TB * (TB + 1);     // [64][65] L_ij being applied
+    double *part = Ls + TB * (TB + 1);   // [4][64]
+    double *xi = part + 4 * TB;          // [64]
+    double *dinvs = xi + TB;             // [64]
+    __shared__ int sh_j;
+    const int T = a.T, ld = a.ld, tid = threadIdx.x;
+    const bool failed = *a.fail != 0;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sh_j = T - 1 - atomicAdd(a.counter + 1, 1);
+        __syncthreads();
+        const int j = sh_j;
+        if (j < 0) return;
+        const int j0 = j * TB;
+        const int c = tid & 63, q = tid >> 6;
+        for (int idx = tid; idx < TB * TB / 2; idx += CT) {
+            const int r = idx >> 5, k2 = (idx & 31) * 2;
+            const double2 v = __ldcg(reinterpret_cast<const double2 *>(a.H + (size_t)(j0 + r) * ld + j0 + k2));
+            Ld[r * (TB + 1) + k2] = v.x;
+            Ld[r * (TB + 1) + k2 + 1] = v.y;
+        }
+        if (tid < TB) dinvs[tid] = __ldcg(a.dinv + j0 + tid);
+        double s = 0.0;
+        for (int i = T - 1; i > j; i--) {
+            // stage L_ij while x_i may still be in flight
+            double2 v[TB * TB / 2 / CT];
+#pragma unroll
+            for (int u = 0; u < TB * TB / 2 / CT; u++) {
+                const int idx = tid + u * CT;
+                const int r = idx >> 5, k2 = (idx & 31) * 2;
+                v[u] = __ldcg(reinterpret_cast<const double2 *>(a.H + (size_t)(i * TB + r) * ld + j0 + k2));
+            }
+#pragma unroll
+            for (int u = 0; u < TB * TB / 2 / CT; u++) {
+                const int idx = tid + u * CT;
+                const int r = idx >> 5, k2 = (idx & 31) * 2;
+                Ls[r * (TB + 1) + k2] = v[u].x;
+                Ls[r * (TB + 1) + k2 + 1] = v[u].y;
+            }
+            wait_flag(a.xflags + i, a.epoch);
+            if (tid < TB) xi[tid] = __ldcg(a.b + i * TB + tid);
+            __syncthreads();
+#pragma unroll
+            for (int p = 0; p < 16; p++) s = fma(Ls[(q * 16 + p) * (TB + 1) + c], xi[q * 16 + p], s);
+            __syncthreads();
+        }
+        part[q * TB + c] = s;
+        __syncthreads();
+        if (tid < 32) {
+            double v0 = __ldcg(a.b + j0 + tid) - (part[tid] + part[TB + tid] + part[2 * TB + tid] + part[3 * TB + tid]);
+            double v1 = __ldcg(a.b + j0 + 32 + tid) - (part[32 + tid] + part[TB + 32 + tid] + part[2 * TB + 32 + tid] + part[3 * TB + 32 + tid]);
+#pragma unroll 4
+            for (int c2 = TB - 1; c2 >= 0; c2--) {
+                const double src = (c2 < 32) ? v0 : v1;
+                const double xc = __shfl_sync(0xffffffffu, src, c2 & 31) * dinvs[c2];
+                // x_r -= L[c2][r] * x_c2 for r < c2
+                if (tid < c2) v0 = fma(-Ld[c2 * (TB + 1) + tid], xc, v0);
+                if (tid + 32 < c2) v1 = fma(-Ld[c2 * (TB + 1) + tid + 32], xc, v1);
+                if (tid == (c2 & 31)) {
+                    if (c2 < 32) v0 = xc; else v1 = xc;
+                }
+            }
+            a.b[j0 + tid] = v0;
+            a.b[j0 + 32 + tid] = v1;
+            if (j0 + tid < a.n) a.dx[j0 + tid] = failed ? 0.0f : (float)v0;
+            if (j0 + 32 + tid < a.n) a.dx[j0 + 32 + tid] = failed ? 0.0f : (float)v1;
+        }
+        publish_flag(a.xflags + j, a.epoch);
+    }
+}
+
+cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx, int *scratch,
+                                double *dinv, int epoch, cudaStream_t st, int *launches) {
+    // scratch (ints): [0..1] counters, [2] fail, [16 .. 16+T) xflags, [16+T ..) (T+1)*T tile flags
+    const int T = npad / TB;
+    cudaError_t err = cudaMemsetAsync(scratch, 0, 16 * sizeof(int), st);
+    if (err != cudaSuccess) return err;
+    CholArgs a;
+    a.H = H;
+    a.b = b;
+    a.ld = npad;
+    a.T = T;
+    a.n = n;
+    a.lm = lm;
+    a.ep = ep;
+    a.counter = scratch;
+    a.fail = scratch + 2;
+    a.xflags = scratch + 16;
+    a.flags = scratch + 16 + T;
+    a.epoch = epoch;
+    a.dx = dx;
+    a.dinv = dinv;
+    const size_t sm = (size_t)(2 * TB * LD + 2 * TB + 32 * 34 + TB * DL) * sizeof(double);
+    err = cudaFuncSetAttribute(chol_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (err != cudaSuccess) return err;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int total = T * (T + 1) / 2 + T;
+    // small systems are latency-bound: one CTA per SM gives the critical-path tiles a whole fp64 pipe;
+    // large ones are throughput-bound: two CTAs per SM overlap tile loads with the tile GEMMs
+    const int ctas = (T >= 40 ? 2 : 1) * sms;
+    const int grid = total < ctas ? total : ctas;
+    chol_factor_kernel<<<grid, CT, sm, st>>>(a);
+    const size_t smb = (size_t)(2 * TB * (TB + 1) + 6 * TB) * sizeof(double);
+    err = cudaFuncSetAttribute(chol_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+    if (err != cudaSuccess) return err;
+    chol_backward_kernel<<<T < sms ? T : sms, CT, smb, st>>>(a);
+    if (launches) *launches += 2;
     return cudaGetLastError();
+}
+
+size_t chol_scratch_ints(int npad) {
+    const int T = npad / TB;
+    return 16 + (size_t)T + (size_t)(T + 1) * T;
 }
 
 }  // namespace vba

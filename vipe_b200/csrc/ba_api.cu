@@ -31,6 +31,7 @@ struct vipe_ba_plan {
     int rank = 0, world = 1;
     int n = 0, npad = 0;
     int NT = 256, PPT = 1, ntile = 0;
+    bool packed = false;  // linearize2 (pixel-pair) kernel
     int NTm = 256, PPTm = 1, ntile_m = 0;  // motion-only tile shape (no staging buffer => always the widest)
     int k_lo = 0, k_hi = 0, dmax = 0;
     int64_t n_triples = 0;
@@ -148,7 +149,10 @@ extern "C" int vipe_ba_plan_create(const int64_t *ii, const int64_t *jj, int64_t
     p->dmax = 0;
     for (int k = p->k_lo; k < p->k_hi; k++) p->dmax = std::max(p->dmax, p->fptr[k + 1] - p->fptr[k]);
 
-    if (!tile_config(p->HW, std::max(p->dmax, 1), false, p->NT, p->PPT)) {
+    if (tile_config2(p->HW, std::max(p->dmax, 1), false, p->NT)) {
+        p->packed = true;
+        p->PPT = 2;
+    } else if (!tile_config(p->HW, std::max(p->dmax, 1), false, p->NT, p->PPT)) {
         delete p;
         return fail("a source frame has too many outgoing edges for the shared-memory staging buffer");
     }
@@ -308,7 +312,10 @@ static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void 
     la.gpart = (float *)(w + p->off_gpart);
     la.qbuf = (float *)(w + p->off_q);
     la.qwbuf = (float *)(w + p->off_qw);
-    VBA_CUDA(launch_linearize(la, nframes, std::max(p->dmax, 1), motion_only != 0, p->NT, p->PPT, st));
+    if (p->packed)
+        VBA_CUDA(launch_linearize2(la, nframes, std::max(p->dmax, 1), motion_only != 0, p->NT, st));
+    else
+        VBA_CUDA(launch_linearize(la, nframes, std::max(p->dmax, 1), motion_only != 0, p->NT, p->PPT, st));
     p->launches++;
     if (mid) VBA_CUDA(cudaEventRecord(mid, st));
 

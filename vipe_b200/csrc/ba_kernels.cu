@@ -265,30 +265,38 @@ __global__ void __launch_bounds__(NT) linearize_kernel(const LinArgs a) {
         decode_pair(p, m, mp);
         const float *Um = U + (size_t)6 * m * TILE;
         const float *Up = U + (size_t)6 * mp * TILE;
-        float g[36];
+        // each lane takes pixel PAIRS (float2 loads, packed FFMA2): lanes stride over the tile 64 pixels at a time
+        float2 g2[36];
 #pragma unroll
-        for (int q = 0; q < 36; q++) g[q] = 0.0f;
-        float sb[6] = {0, 0, 0, 0, 0, 0};
+        for (int q = 0; q < 36; q++) g2[q] = make_float2(0.0f, 0.0f);
+        float2 sb2[6];
+#pragma unroll
+        for (int q = 0; q < 6; q++) sb2[q] = make_float2(0.0f, 0.0f);
         const bool diag = (m == mp);
 #pragma unroll 2
-        for (int px = lane; px < TILE; px += 32) {
-            const float q = Qs[px];
-            float ua[6], ub[6];
+        for (int px = 2 * lane; px < TILE; px += 64) {
+            const float2 q = *reinterpret_cast<const float2 *>(Qs + px);
+            float2 ua[6], ub[6];
 #pragma unroll
             for (int r = 0; r < 6; r++) {
-                ua[r] = Um[r * TILE + px] * q;
-                ub[r] = Up[r * TILE + px];
+                ua[r] = fmul2(*reinterpret_cast<const float2 *>(Um + r * TILE + px), q);
+                ub[r] = *reinterpret_cast<const float2 *>(Up + r * TILE + px);
             }
 #pragma unroll
             for (int r = 0; r < 6; r++)
 #pragma unroll
-                for (int c2 = 0; c2 < 6; c2++) g[r * 6 + c2] = fmaf(ua[r], ub[c2], g[r * 6 + c2]);
+                for (int c2 = 0; c2 < 6; c2++) g2[r * 6 + c2] = ffma2(ua[r], ub[c2], g2[r * 6 + c2]);
             if (diag) {
-                const float w = Ws[px];
+                const float2 w = *reinterpret_cast<const float2 *>(Ws + px);
 #pragma unroll
-                for (int r = 0; r < 6; r++) sb[r] = fmaf(ua[r], w, sb[r]);
+                for (int r = 0; r < 6; r++) sb2[r] = ffma2(ua[r], w, sb2[r]);
             }
         }
+        float g[36], sb[6];
+#pragma unroll
+        for (int q = 0; q < 36; q++) g[q] = g2[q].x + g2[q].y;
+#pragma unroll
+        for (int q = 0; q < 6; q++) sb[q] = sb2[q].x + sb2[q].y;
         float v32[32];
 #pragma unroll
         for (int q = 0; q < 32; q++) v32[q] = g[q];

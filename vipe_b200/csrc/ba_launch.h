@@ -11,6 +11,9 @@ namespace vba {
 bool tile_config(int HW, int dmax, bool motion, int &NT, int &PPT);
 
 cudaError_t launch_linearize(const LinArgs &a, int nframes, int dmax, bool motion, int NT, int PPT, cudaStream_t st);
+// packed 2-pixels-per-thread variant (ba_linearize2.cu); needs an even HW.  TILE = 2 * NT.
+bool tile_config2(int HW, int dmax, bool motion, int &NT);
+cudaError_t launch_linearize2(const LinArgs &a, int nframes, int dmax, bool motion, int NT, cudaStream_t st);
 cudaError_t launch_frame_reduce(const ReduceArgs &a, int nframes, int dmax, cudaStream_t st);
 cudaError_t launch_backsub(const BackArgs &a, int nframes, int dmax, cudaStream_t st);
 cudaError_t launch_pose_retr(float *poses, const float *dx, int t0, int t1, cudaStream_t st);

@@ -89,6 +89,9 @@ typedef struct vipe_ba_tensors {
 int vipe_ba_run(const vipe_ba_plan *plan, const vipe_ba_tensors *t, void *workspace, int iterations, float lm,
                 float ep, int motion_only, void *stream);
 
+/* CUDA-graph replay of repeated vipe_ba_run calls with identical arguments (default on). */
+int vipe_ba_set_graphs(vipe_ba_plan *plan, int on);
+
 /*
  * The same iteration split at its one exchange point, for keyframe-sharded multi-GPU runs:
  *   vipe_ba_linearize   : stages 1-3 on this rank's source frames -> partial reduced camera system

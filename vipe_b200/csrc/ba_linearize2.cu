@@ -280,15 +280,19 @@ __global__ void __launch_bounds__(2 * NT) linearize2_kernel(const LinArgs a) {
                     ualo[r] = fmul2(make_float2(ua4[r].x, ua4[r].y), make_float2(q4.x, q4.y));
                     uahi[r] = fmul2(make_float2(ua4[r].z, ua4[r].w), make_float2(q4.z, q4.w));
                 }
+                // the next column block is loaded while the current one is consumed (one LDS latency per step instead of six)
+                float4 ubn = *reinterpret_cast<const float4 *>(Up + px);
 #pragma unroll
                 for (int c2 = 0; c2 < 6; c2++) {
-                    const float4 ub4 = *reinterpret_cast<const float4 *>(Up + c2 * TILE + px);
+                    const float4 ub4 = ubn;
+                    if (c2 < 5) ubn = *reinterpret_cast<const float4 *>(Up + (c2 + 1) * TILE + px);
+                    else if (diag) ubn = *reinterpret_cast<const float4 *>(Ws + px);
                     const float2 blo = make_float2(ub4.x, ub4.y), bhi = make_float2(ub4.z, ub4.w);
 #pragma unroll
                     for (int r = 0; r < 6; r++) g2[r * 6 + c2] = ffma2(uahi[r], bhi, ffma2(ualo[r], blo, g2[r * 6 + c2]));
                 }
                 if (diag) {
-                    const float4 w4 = *reinterpret_cast<const float4 *>(Ws + px);
+                    const float4 w4 = ubn;
                     const float2 wlo = make_float2(w4.x, w4.y), whi = make_float2(w4.z, w4.w);
 #pragma unroll
                     for (int r = 0; r < 6; r++) sb2[r] = ffma2(uahi[r], whi, ffma2(ualo[r], wlo, sb2[r]));
@@ -332,10 +336,21 @@ static size_t lin2_smem_bytes(int d, int NT, bool motion) {
 
 bool tile_config2(int HW, int dmax, bool motion, int &NT) {
     if (HW % 2 != 0) return false;
-    const size_t cap = 200 * 1024;
+    // measured at C3: one 512-thread CTA per SM on a 512-pixel tile (0.27 ms) beats two 256-thread CTAs on 256-pixel
+    // tiles (0.35 ms), so the big tile is tried first; smaller ones when the staging buffer would not fit
+    const size_t cap2 = 110 * 1024, cap1 = 200 * 1024;
     const int cand[] = {256, 128, 64, 32};
+    if (lin2_smem_bytes(dmax, 256, motion) <= cap1) {
+        NT = 256;
+        return true;
+    }
     for (int nt : cand) {
-        if (lin2_smem_bytes(dmax, nt, motion) > cap) continue;
+        if (nt == 256 || lin2_smem_bytes(dmax, nt, motion) > cap2) continue;
+        NT = nt;
+        return true;
+    }
+    for (int nt : cand) {
+        if (lin2_smem_bytes(dmax, nt, motion) > cap1) continue;
         NT = nt;
         return true;
     }

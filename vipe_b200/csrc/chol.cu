@@ -520,11 +520,157 @@ __global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Systems of at most two tiles (6P <= 128: the frontend window and the inner filler) are solved by ONE CTA with
+// everything resident in shared memory: no ready flags, no hops through L2, one launch.
+//   [A00 .  ]   potrf(A00) -> L10 = A10 L00^-T -> A11 -= L10 L10^T -> potrf(A11) -> two triangular solves
+//   [A10 A11]
+__device__ void smem_trsv_fwd(const double *L, const double *dinv, double *v, int lane) {
+    // L row-major [64][DL]; solves L y = v in place (one warp)
+    double v0 = v[lane], v1 = v[lane + 32];
+    for (int c = 0; c < TB; c++) {
+        const double yc = __shfl_sync(0xffffffffu, (c < 32) ? v0 : v1, c & 31) * dinv[c];
+        if (lane > c) v0 = fma(-L[lane * DL + c], yc, v0);
+        if (lane + 32 > c) v1 = fma(-L[(lane + 32) * DL + c], yc, v1);
+        if (lane == (c & 31)) {
+            if (c < 32) v0 = yc; else v1 = yc;
+        }
+    }
+    v[lane] = v0;
+    v[lane + 32] = v1;
+}
+__device__ void smem_trsv_bwd(const double *L, const double *dinv, double *v, int lane) {
+    // solves L^T x = v in place (one warp)
+    double v0 = v[lane], v1 = v[lane + 32];
+    for (int c = TB - 1; c >= 0; c--) {
+        const double xc = __shfl_sync(0xffffffffu, (c < 32) ? v0 : v1, c & 31) * dinv[c];
+        if (lane < c) v0 = fma(-L[c * DL + lane], xc, v0);
+        if (lane + 32 < c) v1 = fma(-L[c * DL + lane + 32], xc, v1);
+        if (lane == (c & 31)) {
+            if (c < 32) v0 = xc; else v1 = xc;
+        }
+    }
+    v[lane] = v0;
+    v[lane + 32] = v1;
+}
+
+__global__ void __launch_bounds__(CT) chol_small_kernel(const double *__restrict__ H, const double *__restrict__ b, int n,
+                                                        int ld, int T, float lm, float ep, float *__restrict__ dx) {
+    extern __shared__ __align__(16) double sm[];
+    double *A00 = sm;                   // [64][DL]
+    double *A10 = A00 + TB * DL;        // [64][DL]
+    double *A11 = A10 + TB * DL;        // [64][DL]
+    double *Lt = A11 + TB * DL;         // [64][LD]  L00 transposed ([c][q]) for the tile solve
+    double *dinv0 = Lt + TB * LD;       // [64]
+    double *dinv1 = dinv0 + TB;         // [64]
+    double *col = dinv1 + TB;           // [64]
+    double *Ltd = col + TB;             // [32][34]
+    double *rhs = Ltd + 32 * 34;        // [128]
+    __shared__ int sh_ok;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sh_ok = 1;
+    for (int idx = tid; idx < TB * TB; idx += CT) {
+        const int r = idx >> 6, c = idx & 63;
+        double v = (c <= r) ? H[(size_t)r * ld + c] : 0.0;
+        if (r == c && r < n) v += (double)ep + (double)lm * v;  // geom_kernels.cu:1176
+        A00[r * DL + c] = v;
+        if (T == 2) {
+            A10[r * DL + c] = H[(size_t)(TB + r) * ld + c];
+            double w = (c <= r) ? H[(size_t)(TB + r) * ld + TB + c] : 0.0;
+            if (r == c && TB + r < n) w += (double)ep + (double)lm * w;
+            A11[r * DL + c] = w;
+        }
+    }
+    for (int i = tid; i < T * TB; i += CT) rhs[i] = b[i];
+    __syncthreads();
+    bool ok = tile_potrf(A00, dinv0, col, Ltd, &sh_ok);
+    if (T == 2) {
+        for (int idx = tid; idx < TB * TB; idx += CT) {
+            const int r = idx >> 6, c = idx & 63;
+            Lt[c * LD + r] = (c <= r) ? A00[r * DL + c] : 0.0;
+        }
+        __syncthreads();
+        tile_trsm(A10, Lt, dinv0);
+        {   // A11 -= L10 L10^T (lower part is enough)
+            const int r0 = (tid >> 4) * 4, c0 = (tid & 15) * 4;
+            double acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) acc[a][q] = 0.0;
+            if (c0 <= r0 + 3) {
+#pragma unroll 4
+                for (int k = 0; k < TB; k++) {
+                    double av[4], bv[4];
+#pragma unroll
+                    for (int a = 0; a < 4; a++) av[a] = A10[(r0 + a) * DL + k];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) bv[q] = A10[(c0 + q) * DL + k];
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int q = 0; q < 4; q++) acc[a][q] = fma(av[a], bv[q], acc[a][q]);
+                }
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) A11[(r0 + a) * DL + c0 + q] -= acc[a][q];
+            }
+        }
+        __syncthreads();
+        ok = tile_potrf(A11, dinv1, col, Ltd, &sh_ok) && ok;
+    }
+    if (!ok) {  // failed factorisation => zero update (geom_kernels.cu:1186-1188)
+        for (int i = tid; i < n; i += CT) dx[i] = 0.0f;
+        return;
+    }
+    // forward: y0 = L00^-1 b0 ; y1 = L11^-1 (b1 - L10 y0)
+    if (warp == 0) smem_trsv_fwd(A00, dinv0, rhs, lane);
+    __syncthreads();
+    if (T == 2) {
+        if (tid < TB) {
+            double s = 0.0;
+            for (int k = 0; k < TB; k++) s = fma(A10[tid * DL + k], rhs[k], s);
+            rhs[TB + tid] -= s;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            smem_trsv_fwd(A11, dinv1, rhs + TB, lane);
+            smem_trsv_bwd(A11, dinv1, rhs + TB, lane);
+        }
+        __syncthreads();
+        if (tid < TB) {
+            double s = 0.0;
+            for (int k = 0; k < TB; k++) s = fma(A10[k * DL + tid], rhs[TB + k], s);
+            rhs[tid] -= s;
+        }
+        __syncthreads();
+    }
+    if (warp == 0) smem_trsv_bwd(A00, dinv0, rhs, lane);
+    __syncthreads();
+    for (int i = tid; i < n; i += CT) dx[i] = (float)rhs[i];
+}
+
+static cudaError_t launch_small_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx, cudaStream_t st,
+                                      int *launches) {
+    const size_t sm = (size_t)(3 * TB * DL + TB * LD + 3 * TB + 32 * 34 + 2 * TB) * sizeof(double);
+    cudaError_t err = cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (err != cudaSuccess) return err;
+    chol_small_kernel<<<1, CT, sm, st>>>(H, b, n, npad, npad / TB, lm, ep, dx);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx, int *scratch,
                                 double *dinv, int epoch, cudaStream_t st, int *launches) {
     // scratch (ints): [0..1] counters, [2] fail, [16 .. 16+T) xflags, [16+T ..) (T+1)*T tile flags
     const int T = npad / TB;
-    cudaError_t err = cudaMemsetAsync(scratch, 0, 16 * sizeof(int), st);
+    (void)epoch;
+    if (T <= 2) return launch_small_solve(H, b, n, npad, lm, ep, dx, st, launches);
+    // ready flags, counters and the failure flag are reset by one small memset per solve (graph-capturable, and the
+    // flags never carry state from one solve to the next)
+    cudaError_t err = cudaMemsetAsync(scratch, 0, chol_scratch_ints(npad) * sizeof(int), st);
     if (err != cudaSuccess) return err;
     CholArgs a;
     a.H = H;
@@ -538,7 +684,7 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     a.fail = scratch + 2;
     a.xflags = scratch + 16;
     a.flags = scratch + 16 + T;
-    a.epoch = epoch;
+    a.epoch = 1;
     a.dx = dx;
     a.dinv = dinv;
     const size_t sm = (size_t)(2 * TB * LD + 2 * TB + 32 * 34 + TB * DL) * sizeof(double);

@@ -13,7 +13,7 @@ using namespace vba;
 // ---- micro timing of the tile primitives (single CTA), cycles via clock64
 __global__ void __launch_bounds__(CT) micro_kernel(double *out, long long *clk) {
     extern __shared__ __align__(16) double sm[];
-    double *As = sm, *Bs = sm + TB * LD, *col = Bs + TB * LD, *dinv = col + TB, *Ltd = dinv + TB;
+    double *As = sm, *Bs = sm + TB * RS, *col = Bs + TB * RS, *dinv = col + TB, *Ltd = dinv + TB;
     __shared__ int sh_ok;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // SPD tile in As (row-major DL)
@@ -53,8 +53,8 @@ __global__ void __launch_bounds__(CT) micro_kernel(double *out, long long *clk) 
     long long t5 = clock64();
     tile_trsm(Bs, As, dinv);
     long long t6 = clock64();
-    double acc[4][4];
-    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) acc[r][c] = r + c;
+    double acc[8][2];
+    for (int r = 0; r < 8; r++) for (int c = 0; c < 2; c++) acc[r][c] = r + c;
     __syncthreads();
     long long t7 = clock64();
     tile_gemm_sub(acc, As, Bs);
@@ -63,14 +63,14 @@ __global__ void __launch_bounds__(CT) micro_kernel(double *out, long long *clk) 
     if (tid == 0) {
         clk[0] = t1 - t0; clk[1] = t3 - t2; clk[2] = t4 - t3; clk[3] = t6 - t5; clk[4] = t8 - t7;
     }
-    out[64 + tid] = acc[0][0] + acc[3][3] + Bs[tid];
+    out[64 + tid] = acc[0][0] + acc[7][1] + Bs[tid];
 }
 
 int main(int argc, char **argv) {
     if (argc > 1 && atoi(argv[1]) == 0) {
         double *out; long long *clk, h[5];
         cudaMalloc(&out, 4096 * 8); cudaMalloc(&clk, 256);
-        const size_t smb = (size_t)(2 * TB * LD + 2 * TB + 32 * 34 + TB * DL) * sizeof(double);
+        const size_t smb = (size_t)(2 * TB * RS + 2 * TB + 32 * 34 + TB * DL) * sizeof(double);
         cudaFuncSetAttribute(micro_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
         for (int r = 0; r < 3; r++) {
             micro_kernel<<<1, CT, smb>>>(out, clk);

@@ -93,37 +93,56 @@ struct CholArgs {
     double *dinv;  // [npad] 1 / diag(L)
 };
 
-// thread (tx, ty) owns rows ty*4..+3 and columns tx*4..+3 of a 64x64 tile; tx = tid / 16 so that the 16 owners of
-// a column group share a warp (pivot broadcast by shuffle)
-#define TX (threadIdx.x >> 4)
-#define TY (threadIdx.x & 15)
-
-// acc -= A * B^T with As/Bs in [k][row] layout (row stride LD); thread (TX, TY) owns a 4x4 register tile.
-// Measured on B200: an fp64 outer-product loop fed from shared memory sustains ~26-28 DFMA/clk/SM whether the
-// register tile is 4x4 or 8x8 (45-48 from registers alone, 62 peak), so the small tile wins on registers.
-__device__ __forceinline__ void tile_gemm_sub(double (&acc)[4][4], const double *As, const double *Bs) {
-    const int r0 = TY * 4, c0 = TX * 4;
-#pragma unroll 8
-    for (int k = 0; k < TB; k++) {
-        const double2 a01 = *reinterpret_cast<const double2 *>(As + k * LD + r0);
-        const double2 a23 = *reinterpret_cast<const double2 *>(As + k * LD + r0 + 2);
-        const double2 b01 = *reinterpret_cast<const double2 *>(Bs + k * LD + c0);
-        const double2 b23 = *reinterpret_cast<const double2 *>(Bs + k * LD + c0 + 2);
-        const double av[4] = {a01.x, a01.y, a23.x, a23.y};
-        const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+// Tile GEMM on the fp64 tensor cores (mma.sync.m8n8k4.f64 -> DMMA).  Measured on B200: DMMA issues at the full
+// 64 FMA/clk/SM with one instruction per 256 FMAs, whereas a DFMA outer-product loop fed from shared memory
+// sustains only 26-28 FMA/clk/SM (operand delivery), so the trailing updates of the factorisation use DMMA.
+//   acc -= A * B^T, A = L_ik and B = L_jk as ROW-MAJOR tiles in shared memory with row stride RS = 68 doubles
+//   (68 = 4 mod 16 makes both fragment loads conflict-free: lane l reads [l/4][k0 + l%4]).
+// Warp w owns output columns 8w..8w+7 and all 64 rows: 8 accumulator fragments; the C fragment of m-tile mt holds
+// rows 8mt + l/4, columns 8w + 2(l%4) + {0,1}.
+constexpr int RS = 68;
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void tile_gemm_sub(double (&acc)[8][2], const double *As, const double *Bs) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double *ap = As + (lane >> 2) * RS + (lane & 3);
+    const double *bp = Bs + (8 * warp + (lane >> 2)) * RS + (lane & 3);
+#pragma unroll 4
+    for (int k0 = 0; k0 < TB; k0 += 4) {
+        const double bneg = -bp[k0];
 #pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-            for (int b = 0; b < 4; b++) acc[a][b] = fma(-av[a], bv[b], acc[a][b]);
+        for (int mt = 0; mt < 8; mt++) dmma884(acc[mt], ap[mt * 8 * RS + k0], bneg);
     }
 }
 
-// register tile (acc) -> row-major shared tile S[64][DL]
-__device__ __forceinline__ void acc_to_smem(const double (&acc)[4][4], double *S) {
+// fragment-distributed tile (acc) -> row-major shared tile S[64][DL]
+__device__ __forceinline__ void acc_to_smem(const double (&acc)[8][2], double *S) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int r = 0; r < 4; r++)
+    for (int mt = 0; mt < 8; mt++) {
+        double *d = S + (8 * mt + (lane >> 2)) * DL + 8 * warp + 2 * (lane & 3);
+        d[0] = acc[mt][0];
+        d[1] = acc[mt][1];
+    }
+}
+
+// load a 64x64 tile (global row-major, leading dim ld) into shared memory row-major with stride RS
+__device__ __forceinline__ void load_tile_R(double *S, const double *__restrict__ G, int ld) {
+    double2 v[TB * TB / 2 / CT];
 #pragma unroll
-        for (int c = 0; c < 4; c++) S[(TY * 4 + r) * DL + TX * 4 + c] = acc[r][c];
+    for (int u = 0; u < TB * TB / 2 / CT; u++) {
+        const int idx = threadIdx.x + u * CT;
+        const int r = idx >> 5, k2 = (idx & 31) * 2;
+        v[u] = __ldcg(reinterpret_cast<const double2 *>(G + (size_t)r * ld + k2));
+    }
+#pragma unroll
+    for (int u = 0; u < TB * TB / 2 / CT; u++) {
+        const int idx = threadIdx.x + u * CT;
+        const int r = idx >> 5, k2 = (idx & 31) * 2;
+        *reinterpret_cast<double2 *>(S + r * RS + k2) = v[u];
+    }
 }
 
 // load a 64x64 tile (global row-major, leading dim ld) into shared memory transposed: S[k][row].
@@ -303,9 +322,9 @@ __device__ void tile_trsm(double *X, const double *Lt, const double *dinv) {
 
 __global__ void __launch_bounds__(CT, 2) chol_factor_kernel(const CholArgs a) {
     extern __shared__ __align__(16) double sm[];
-    double *As = sm;             // [64][LD]
-    double *Bs = sm + TB * LD;   // [64][LD]
-    double *col = Bs + TB * LD;  // [64]
+    double *As = sm;             // [64][RS]
+    double *Bs = sm + TB * RS;   // [64][RS]
+    double *col = Bs + TB * RS;  // [64]
     double *dinv = col + TB;     // [64]
     double *Ltd = dinv + TB;     // [32][34] transposed L11 of the diagonal tile
     double *Ct = Ltd + 32 * 34;  // [64][DL] the tile being computed
@@ -383,21 +402,19 @@ __global__ void __launch_bounds__(CT, 2) chol_factor_kernel(const CholArgs a) {
         }
 
         const int i0 = i * TB;
-        // ---- load A_ij into registers (damping on the diagonal of diagonal tiles: geom_kernels.cu:1176)
-        const int tx = TX, ty = TY;
-        double acc[4][4];
+        // ---- load A_ij into the accumulator fragments (damping on the diagonal of diagonal tiles: geom_kernels.cu:1176)
+        double acc[8][2];
+        {
+            const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const double *src = a.H + (size_t)(i0 + ty * 4 + r) * ld + j0 + tx * 4;
-            const double2 v01 = __ldcg(reinterpret_cast<const double2 *>(src));
-            const double2 v23 = __ldcg(reinterpret_cast<const double2 *>(src + 2));
-            acc[r][0] = v01.x, acc[r][1] = v01.y, acc[r][2] = v23.x, acc[r][3] = v23.y;
-        }
-        if (i == j && tx == ty) {
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const int g = i0 + ty * 4 + r;
-                if (g < a.n) acc[r][r] += (double)a.ep + (double)a.lm * acc[r][r];
+            for (int mt = 0; mt < 8; mt++) {
+                const int r = 8 * mt + (lane >> 2), c = 8 * warp + 2 * (lane & 3);
+                const double2 v = __ldcg(reinterpret_cast<const double2 *>(a.H + (size_t)(i0 + r) * ld + j0 + c));
+                acc[mt][0] = v.x, acc[mt][1] = v.y;
+                if (i == j && i0 + r < a.n) {
+                    if (r == c) acc[mt][0] += (double)a.ep + (double)a.lm * acc[mt][0];
+                    if (r == c + 1) acc[mt][1] += (double)a.ep + (double)a.lm * acc[mt][1];
+                }
             }
         }
         TRACE(t, 1);
@@ -406,8 +423,8 @@ __global__ void __launch_bounds__(CT, 2) chol_factor_kernel(const CholArgs a) {
             wait_flag(a.flags + (size_t)i * T + k, a.epoch);
             if (i != j) wait_flag(a.flags + (size_t)j * T + k, a.epoch);
             TRACE(t, 7);
-            load_tile_T(As, a.H + (size_t)i0 * ld + k * TB, ld);
-            if (i != j) load_tile_T(Bs, a.H + (size_t)j0 * ld + k * TB, ld);
+            load_tile_R(As, a.H + (size_t)i0 * ld + k * TB, ld);
+            if (i != j) load_tile_R(Bs, a.H + (size_t)j0 * ld + k * TB, ld);
             __syncthreads();
             tile_gemm_sub(acc, As, (i != j) ? Bs : As);
             __syncthreads();
@@ -687,7 +704,7 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     a.epoch = 1;
     a.dx = dx;
     a.dinv = dinv;
-    const size_t sm = (size_t)(2 * TB * LD + 2 * TB + 32 * 34 + TB * DL) * sizeof(double);
+    const size_t sm = (size_t)(2 * TB * RS + 2 * TB + 32 * 34 + TB * DL) * sizeof(double);
     err = cudaFuncSetAttribute(chol_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (err != cudaSuccess) return err;
     int dev = 0, sms = 148;

@@ -286,6 +286,12 @@ def main():
     it_bytes, lin_bytes = algorithmic_bytes(cfg, E, K, N, HW, cfg.motion_only)
     peak, peak_src = measured_peaks()
 
+    # fp32 work of the fused kernel (it is FMA-bound, not HBM-bound, at backend degrees): ~110 FMA-pipe lane-ops per
+    # edge-pixel for the linearisation + 36 per block pair and frame-pixel for the Schur Gram
+    deg = torch.bincount(pr.ii, minlength=N).double()
+    gram_ops = float((36.0 * deg * (deg + 1) / 2 + 12.0 * deg).sum()) * HW
+    lin_fma_ops = 110.0 * E * HW + (0.0 if cfg.motion_only else gram_ops)
+    FP32_PEAK_TFMA = 34.3  # measured on this pool: FFMA/FFMA2 full-chip micro-benchmark (scripts/ffma2_micro.cu), TFMA/s
     roofline = None
     if stage_iters > 0:
         lin_ms = stage_ms[0] / stage_iters  # average duration of one linearise launch (incl. the system clear)
@@ -295,6 +301,10 @@ def main():
                     "traffic": None, "algorithmic_bytes_per_launch": lin_bytes, "avg_launch_ms": lin_ms,
                     "stage_ms_per_iteration": {"linearize_schur": stage_ms[0] / stage_iters, "assemble": stage_ms[1] / stage_iters,
                                                "solve": stage_ms[2] / stage_iters, "backsub_retract": stage_ms[3] / stage_iters},
+                    "compute": {"bound": "fp32 FMA pipe", "fma_lane_ops_per_launch": lin_fma_ops,
+                                "achieved_tfma_s": lin_fma_ops / (lin_ms * 1e-3) / 1e12, "peak_tfma_s": FP32_PEAK_TFMA,
+                                "frac": lin_fma_ops / (lin_ms * 1e-3) / 1e12 / FP32_PEAK_TFMA,
+                                "note": "the fused Jacobian+Schur kernel is FMA-bound at backend degrees; see DESIGN.md section 4"},
                     "whole_iteration": {"algorithmic_bytes": it_bytes,
                                         "achieved_gbs": it_bytes * cfg.iters * clips * args.steps / (total_ms * 1e-3) / 1e9 / max(world, 1)}}
         prof = ROOT / "profiles" / "traffic.json"

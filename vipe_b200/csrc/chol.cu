@@ -86,6 +86,7 @@ struct CholArgs {
     float lm, ep;
     int *flags;    // [(T+1) x T] tile ready flags, value == epoch when ready; row T is the rhs row
     int *xflags;   // [T] ready flags of the backward substitution
+    int *preflags; // [T] tile (j+1, j) is available BEFORE its solve against L_jj, parked in the unused upper tile (j, j+1)
     int *counter;  // [2] tile counters (factorisation, backward), zero on entry
     int *fail;     // zero on entry
     int epoch;
@@ -277,7 +278,7 @@ __device__ bool tile_potrf(double *D, double *dinv, double *colbuf, double *Lt, 
 
 // X[64][DL] (row-major, shared) <- X L^-T; L is given transposed, Lt[c * LD + q] = L[q][c] (load_tile_T layout),
 // dinv[64] = 1 / diag(L).  All threads must call.
-__device__ void tile_trsm(double *X, const double *Lt, const double *dinv) {
+__device__ __noinline__ void tile_trsm(double *X, const double *Lt, const double *dinv) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double a[32];
     if (warp < 2) {  // X1 = A1 L11^-T, one row per lane
@@ -320,7 +321,9 @@ __device__ void tile_trsm(double *X, const double *Lt, const double *dinv) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(CT, 2) chol_factor_kernel(const CholArgs a) {
+// MINB = 1: latency-bound sizes, the whole register file for the unrolled register kernels; MINB = 2: throughput-bound
+template <int MINB>
+__global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a) {
     extern __shared__ __align__(16) double sm[];
     double *As = sm;             // [64][RS]
     double *Bs = sm + TB * RS;   // [64][RS]
@@ -420,6 +423,33 @@ __global__ void __launch_bounds__(CT, 2) chol_factor_kernel(const CholArgs a) {
         TRACE(t, 1);
         // ---- left-looking updates
         for (int k = 0; k < j; k++) {
+            if (MINB == 1 && i == j && k == j - 1) {
+                // Critical path: the diagonal tile's last update needs L_{j,j-1}.  Instead of waiting for the CTA that
+                // owns that tile to solve and publish it (one more trip through L2), take its pre-solve copy -- ready
+                // long before -- and do the tile solve here as soon as L_{j-1,j-1} appears.
+                const int kk0 = k * TB;
+                wait_flag(a.preflags + k, a.epoch);
+                for (int idx = tid; idx < TB * TB / 2; idx += CT) {
+                    const int r = idx >> 5, c2 = (idx & 31) * 2;
+                    const double2 v = __ldcg(reinterpret_cast<const double2 *>(a.H + (size_t)(kk0 + r) * ld + j0 + c2));
+                    Ct[r * DL + c2] = v.x;
+                    Ct[r * DL + c2 + 1] = v.y;
+                }
+                wait_flag(a.flags + (size_t)k * T + k, a.epoch);
+                TRACE(t, 7);
+                load_tile_T(Bs, a.H + (size_t)kk0 * ld + kk0, ld);  // Bs[c][q] = L_kk[q][c]
+                if (tid < TB) dinv[tid] = __ldcg(a.dinv + kk0 + tid);
+                __syncthreads();
+                tile_trsm(Ct, Bs, dinv);
+                for (int idx = tid; idx < TB * TB; idx += CT) {
+                    const int r = idx >> 6, c = idx & 63;
+                    As[r * RS + c] = Ct[r * DL + c];
+                }
+                __syncthreads();
+                tile_gemm_sub(acc, As, As);
+                __syncthreads();
+                continue;
+            }
             wait_flag(a.flags + (size_t)i * T + k, a.epoch);
             if (i != j) wait_flag(a.flags + (size_t)j * T + k, a.epoch);
             TRACE(t, 7);
@@ -443,6 +473,13 @@ __global__ void __launch_bounds__(CT, 2) chol_factor_kernel(const CholArgs a) {
             }
             if (tid < TB) a.dinv[j0 + tid] = dinv[tid];
         } else {
+            if (MINB == 1 && i == j + 1) {  // park the pre-solve tile in the upper triangle for the next diagonal tile
+                for (int idx = tid; idx < TB * TB; idx += CT) {
+                    const int r = idx >> 6, c = idx & 63;
+                    a.H[(size_t)(j0 + r) * ld + i0 + c] = Ct[r * DL + c];
+                }
+                publish_flag(a.preflags + j, a.epoch);
+            }
             wait_flag(a.flags + (size_t)j * T + j, a.epoch);
             load_tile_T(As, a.H + (size_t)j0 * ld + j0, ld);  // As[c][q] = L_jj[q][c]
             if (tid < TB) dinv[tid] = __ldcg(a.dinv + j0 + tid);
@@ -681,7 +718,7 @@ static cudaError_t launch_small_solve(double *H, double *b, int n, int npad, flo
 
 cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx, int *scratch,
                                 double *dinv, int epoch, cudaStream_t st, int *launches) {
-    // scratch (ints): [0..1] counters, [2] fail, [16 .. 16+T) xflags, [16+T ..) (T+1)*T tile flags
+    // scratch (ints): [0..1] counters, [2] fail, [16 .. 16+T) xflags, [16+T .. 16+2T) preflags, then (T+1)*T tile flags
     const int T = npad / TB;
     (void)epoch;
     if (T <= 2) return launch_small_solve(H, b, n, npad, lm, ep, dx, st, launches);
@@ -700,12 +737,15 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     a.counter = scratch;
     a.fail = scratch + 2;
     a.xflags = scratch + 16;
-    a.flags = scratch + 16 + T;
+    a.preflags = scratch + 16 + T;
+    a.flags = scratch + 16 + 2 * T;
     a.epoch = 1;
     a.dx = dx;
     a.dinv = dinv;
     const size_t sm = (size_t)(2 * TB * RS + 2 * TB + 32 * 34 + TB * DL) * sizeof(double);
-    err = cudaFuncSetAttribute(chol_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    err = cudaFuncSetAttribute(chol_factor_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (err != cudaSuccess) return err;
+    err = cudaFuncSetAttribute(chol_factor_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (err != cudaSuccess) return err;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -715,7 +755,8 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     // large ones are throughput-bound: two CTAs per SM overlap tile loads with the tile GEMMs
     const int ctas = (T >= 40 ? 2 : 1) * sms;
     const int grid = total < ctas ? total : ctas;
-    chol_factor_kernel<<<grid, CT, sm, st>>>(a);
+    if (T >= 40) chol_factor_kernel<2><<<grid, CT, sm, st>>>(a);
+    else chol_factor_kernel<1><<<grid, CT, sm, st>>>(a);
     const size_t smb = (size_t)(2 * TB * (TB + 1) + 6 * TB) * sizeof(double);
     err = cudaFuncSetAttribute(chol_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
     if (err != cudaSuccess) return err;
@@ -726,7 +767,7 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
 
 size_t chol_scratch_ints(int npad) {
     const int T = npad / TB;
-    return 16 + (size_t)T + (size_t)(T + 1) * T;
+    return 16 + 2 * (size_t)T + (size_t)(T + 1) * T;
 }
 
 }  // namespace vba

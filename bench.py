@@ -231,10 +231,12 @@ def main():
             a[0].copy_(p0)
             a[1].copy_(d0)
 
+    shard_prof = {"events": []} if sharded else None
+
     def step():
         for a in dev_args:
             if sharded:
-                ba_sharded(*a, exchange=True)
+                ba_sharded(*a, exchange=True, profile=shard_prof)
             else:
                 slam_ext.ba(*a)
 
@@ -271,6 +273,10 @@ def main():
                 stage_ms = [x + y for x, y in zip(stage_ms, ms4)]
                 stage_iters += its.value
     barrier()
+    shard_stage = None
+    if sharded:
+        evs = shard_prof["events"][-args.steps * cfg.iters:]
+        shard_stage = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) / len(evs) for i in range(3)]
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -279,6 +285,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     launches = sum(pl.launch_count for pl in plans) * args.steps if plans else None
+    if sharded:
+        # the phased entry points accumulate their launch count in the plan: per step = total / (warm-up + timed steps)
+        launches = int(shard_prof["plan"].launch_count * args.steps / (args.steps + args.warmup))
 
     iters_total = args.steps * cfg.iters * clips
     value = iters_total / (total_ms / 1e3)
@@ -293,7 +302,21 @@ def main():
     lin_fma_ops = 110.0 * E * HW + (0.0 if cfg.motion_only else gram_ops)
     FP32_PEAK_TFMA = 34.3  # measured on this pool: FFMA/FFMA2 full-chip micro-benchmark (scripts/ffma2_micro.cu), TFMA/s
     roofline = None
-    if stage_iters > 0:
+    if sharded:
+        # this rank's share of the edge-pixels (owned source frames) over its own linearise time
+        pl = shard_prof["plan"]
+        lo, hi = pl.owned_range()
+        ptrs, _ = pl.csr()
+        own_E = int(ptrs[hi] - ptrs[lo])
+        own_bytes = 16 * own_E * HW + 12 * (hi - lo) * HW + 28 * N + 8 * own_E
+        lin_ms = shard_stage[0]
+        achieved = own_bytes / (lin_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "vba::linearize2_kernel on rank 0's shard (linearise+Schur+assemble stage)",
+                    "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "algorithmic_bytes_per_launch": own_bytes, "avg_launch_ms": lin_ms,
+                    "stage_ms_per_iteration": {"linearize_schur_assemble": shard_stage[0], "all_reduce": shard_stage[1],
+                                               "solve_backsub_retract": shard_stage[2]}}
+    elif stage_iters > 0:
         lin_ms = stage_ms[0] / stage_iters  # average duration of one linearise launch (incl. the system clear)
         achieved = lin_bytes / (lin_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "vba::linearize_kernel (per-source-frame Jacobian/Hessian + Schur Gram)",

@@ -53,11 +53,14 @@ class CudaShardEngine:
 
 
 def ba_sharded(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, t1, iterations, lm, ep,
-               motion_only, group=None, engine_cls=CudaShardEngine, exchange=True):
+               motion_only, group=None, engine_cls=CudaShardEngine, exchange=True, profile=None):
     """`slam_ext.ba` sharded by source keyframe across the ranks of `group`.
 
     Every rank passes the full tensors (poses are replicated; for targets/weights only the rows of owned edges are
-    read).  On return `poses` is identical on all ranks and, if `exchange`, so are `disps[kx]` and `dz`."""
+    read).  On return `poses` is identical on all ranks and, if `exchange`, so are `disps[kx]` and `dz`.
+
+    `profile`: optional dict; CUDA event pairs around (linearise | all-reduce | solve+update) of every iteration are
+    appended to profile["events"] and the plan is stored in profile["plan"] (bench.py reads them after a sync)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     t0, t1 = int(t0), int(t1)
@@ -65,11 +68,24 @@ def ba_sharded(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, 
     plan = cached_plan(ii.detach().to("cpu", torch.int64).contiguous(), jj.detach().to("cpu", torch.int64).contiguous(),
                        N, ht, wd, t0, t1, rank, world)
     eng = engine_cls(plan, poses, disps, intrinsics, disps_sens, targets, weights, eta, motion_only)
+    if profile is not None:
+        profile["plan"] = plan
+        ev = profile.setdefault("events", [])
     for _ in range(int(iterations)):
+        if profile is not None:
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            e[0].record()
         system = eng.linearize()
+        if profile is not None:
+            e[1].record()
         if world > 1:
             dist.all_reduce(system, op=dist.ReduceOp.SUM, group=group)
+        if profile is not None:
+            e[2].record()
         eng.solve_update(lm, ep)
+        if profile is not None:
+            e[3].record()
+            ev.append(e)
     if exchange and world > 1 and not motion_only:
         exchange_owned_rows(plan, disps, eng.dz, group)
     return [eng.dx, eng.dz]

@@ -222,6 +222,61 @@ __device__ __forceinline__ void warp_trsm32(double (&a)[32], const double *Lt, c
     }
 }
 
+__device__ __noinline__ void tile_trsm_mma(double *X, const double *L, const double *dinv, double *linv8, double *tmp, int nblk, int nrw);
+
+// Tensor-core version of tile_potrf for tiles stored with row stride RS: potrf32 (warp 0, registers) ->
+// L21 = A21 L11^-T (DMMA) -> A22 -= L21 L21^T (DMMA) -> potrf32.  All threads must call.
+__device__ bool tile_potrf_mma(double *D, double *dinv, double *colbuf, double *linv8, double *tmp, int *sh_ok) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double a[32];
+    if (warp == 0) {
+#pragma unroll
+        for (int c = 0; c < 32; c++) a[c] = D[lane * RS + c];
+        double my_inv;
+        const bool ok = warp_potrf32(a, colbuf, lane, my_inv);
+#pragma unroll
+        for (int c = 0; c < 32; c++) D[lane * RS + c] = a[c];
+        dinv[lane] = my_inv;
+        if (!ok && lane == 0) *sh_ok = 0;
+    }
+    __syncthreads();
+    tile_trsm_mma(D + 32 * RS, D, dinv, linv8, tmp, 4, 4);  // rows 32..63, columns 0..31
+    if (warp < 4) {  // A22 -= L21 L21^T: warp w -> columns 32+8w.., 4 row tiles
+        const int fr = lane >> 2, fk = lane & 3;
+        double acc[4][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) {
+            const double2 v = *reinterpret_cast<const double2 *>(D + (32 + 8 * mt + fr) * RS + 32 + 8 * warp + 2 * fk);
+            acc[mt][0] = v.x, acc[mt][1] = v.y;
+        }
+        const double *bp = D + (32 + 8 * warp + fr) * RS + fk;
+        const double *ap = D + (32 + fr) * RS + fk;
+#pragma unroll 2
+        for (int k0 = 0; k0 < 32; k0 += 4) {
+            const double bneg = -bp[k0];
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) dmma884(acc[mt], ap[mt * 8 * RS + k0], bneg);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++)
+            *reinterpret_cast<double2 *>(D + (32 + 8 * mt + fr) * RS + 32 + 8 * warp + 2 * fk) = make_double2(acc[mt][0], acc[mt][1]);
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int c = 0; c < 32; c++) a[c] = D[(32 + lane) * RS + 32 + c];
+        double my_inv;
+        const bool ok = warp_potrf32(a, colbuf, lane, my_inv);
+#pragma unroll
+        for (int c = 0; c < 32; c++) D[(32 + lane) * RS + 32 + c] = a[c];
+        dinv[32 + lane] = my_inv;
+        if (!ok && lane == 0) *sh_ok = 0;
+    }
+    __syncthreads();
+    return *sh_ok != 0;
+}
+
 // D[64][DL] (row-major, shared): factorise the lower triangle in place, write 1/diag to dinv[64].
 // 2x2 blocking: potrf32 (warp 0) -> trsm32 (warp 1) -> syrk (all) -> potrf32 (warp 0).  All threads must call.
 __device__ bool tile_potrf(double *D, double *dinv, double *colbuf, double *Lt, int *sh_ok) {
@@ -321,6 +376,66 @@ __device__ __noinline__ void tile_trsm(double *X, const double *Lt, const double
     __syncthreads();
 }
 
+// X <- X L^-T on the fp64 tensor cores.  X[64][RS] and L[64][RS] (lower, row-major) live in shared memory.
+// Column blocks of 8:  S_b = X_b - sum_{b'<b} X_b' L_{b,b'}^T  (DMMA),  X_b = S_b inv(L_bb)^T  (DMMA with the 8x8
+// inverses of the diagonal blocks, computed here by 64 threads).  Warp w owns rows 8w..8w+7 end to end, so the only
+// synchronisation inside is __syncwarp.  ~72 DMMA per warp instead of 2016 dependent DFMA per lane, and a rolled
+// loop instead of 50 KB of unrolled code (which ran mostly out of a cold instruction cache).
+//   linv8: [8][96] scratch (8x8 inverse blocks, row stride 12);  tmp: [8 warps][160] scratch (8x8, row stride 20)
+__device__ __noinline__ void tile_trsm_mma(double *X, const double *L, const double *dinv, double *linv8, double *tmp,
+                                           int nblk = 8, int nrw = 8) {
+    // nblk: column blocks of 8 (size of L / 8);  nrw: row groups of 8 (rows of X / 8), one warp each
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 8 * nblk) {  // inverse of the 8x8 lower-triangular diagonal block b, column c
+        const int b = tid >> 3, c = tid & 7;
+        double x[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            double s = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int p = 0; p < 8; p++)
+                if (p < r && p >= c) s = fma(-L[(8 * b + r) * RS + 8 * b + p], x[p], s);
+            x[r] = (r >= c) ? s * dinv[8 * b + r] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++) linv8[b * 96 + r * 12 + c] = x[r];
+    }
+    __syncthreads();
+    const int fr = lane >> 2, fk = lane & 3;  // fragment row / k index
+    double *xrow = X + (8 * warp + fr) * RS;
+    double *tw = tmp + warp * 160;
+#pragma unroll 1
+    for (int b = 0; b < nblk && warp < nrw; b++) {
+        double acc0[2], acc1[2] = {0.0, 0.0};
+        {
+            const double2 v = *reinterpret_cast<const double2 *>(xrow + 8 * b + 2 * fk);
+            acc0[0] = v.x, acc0[1] = v.y;
+        }
+        const double *lrow = L + (8 * b + fr) * RS + fk;
+#pragma unroll 1
+        for (int bp = 0; bp < b; bp++) {  // two independent accumulation chains
+            dmma884(acc0, xrow[8 * bp + fk], -lrow[8 * bp]);
+            dmma884(acc1, xrow[8 * bp + 4 + fk], -lrow[8 * bp + 4]);
+        }
+        *reinterpret_cast<double2 *>(tw + fr * 20 + 2 * fk) = make_double2(acc0[0] + acc1[0], acc0[1] + acc1[1]);
+        __syncwarp();
+        double x0[2] = {0.0, 0.0};
+        dmma884(x0, tw[fr * 20 + fk], linv8[b * 96 + fr * 12 + fk]);
+        dmma884(x0, tw[fr * 20 + 4 + fk], linv8[b * 96 + fr * 12 + 4 + fk]);
+        *reinterpret_cast<double2 *>(xrow + 8 * b + 2 * fk) = make_double2(x0[0], x0[1]);
+        __syncwarp();
+    }
+    __syncthreads();
+}
+
+// fragment-distributed tile (acc) -> row-major shared tile S[64][RS]
+__device__ __forceinline__ void acc_to_smem_rs(const double (&acc)[8][2], double *S) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int mt = 0; mt < 8; mt++)
+        *reinterpret_cast<double2 *>(S + (8 * mt + (lane >> 2)) * RS + 8 * warp + 2 * (lane & 3)) = make_double2(acc[mt][0], acc[mt][1]);
+}
+
 // MINB = 1: latency-bound sizes, the whole register file for the unrolled register kernels; MINB = 2: throughput-bound
 template <int MINB>
 __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a) {
@@ -331,6 +446,8 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
     double *dinv = col + TB;     // [64]
     double *Ltd = dinv + TB;     // [32][34] transposed L11 of the diagonal tile
     double *Ct = Ltd + 32 * 34;  // [64][DL] the tile being computed
+    double *linv8 = Ct + TB * DL;  // [8][96]
+    double *tmpw = linv8 + 8 * 96;  // [8][160]
     __shared__ int sh_tile, sh_ok;
     const int T = a.T, ld = a.ld, tid = threadIdx.x;
     const int total = T * (T + 1) / 2 + T;  // lower tiles + one rhs tile per column
@@ -429,23 +546,13 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
                 // long before -- and do the tile solve here as soon as L_{j-1,j-1} appears.
                 const int kk0 = k * TB;
                 wait_flag(a.preflags + k, a.epoch);
-                for (int idx = tid; idx < TB * TB / 2; idx += CT) {
-                    const int r = idx >> 5, c2 = (idx & 31) * 2;
-                    const double2 v = __ldcg(reinterpret_cast<const double2 *>(a.H + (size_t)(kk0 + r) * ld + j0 + c2));
-                    Ct[r * DL + c2] = v.x;
-                    Ct[r * DL + c2 + 1] = v.y;
-                }
+                load_tile_R(As, a.H + (size_t)kk0 * ld + j0, ld);  // pre-solve copy of tile (j, j-1), parked at (j-1, j)
                 wait_flag(a.flags + (size_t)k * T + k, a.epoch);
                 TRACE(t, 7);
-                load_tile_T(Bs, a.H + (size_t)kk0 * ld + kk0, ld);  // Bs[c][q] = L_kk[q][c]
+                load_tile_R(Bs, a.H + (size_t)kk0 * ld + kk0, ld);  // L_kk, row-major
                 if (tid < TB) dinv[tid] = __ldcg(a.dinv + kk0 + tid);
                 __syncthreads();
-                tile_trsm(Ct, Bs, dinv);
-                for (int idx = tid; idx < TB * TB; idx += CT) {
-                    const int r = idx >> 6, c = idx & 63;
-                    As[r * RS + c] = Ct[r * DL + c];
-                }
-                __syncthreads();
+                tile_trsm_mma(As, Bs, dinv, linv8, tmpw);
                 tile_gemm_sub(acc, As, As);
                 __syncthreads();
                 continue;
@@ -459,37 +566,37 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
             tile_gemm_sub(acc, As, (i != j) ? Bs : As);
             __syncthreads();
         }
-        acc_to_smem(acc, Ct);
+        acc_to_smem_rs(acc, As);
         __syncthreads();
         TRACE(t, 2);
         if (i == j) {
-            const bool ok = tile_potrf(Ct, dinv, col, Ltd, &sh_ok);
+            const bool ok = tile_potrf_mma(As, dinv, col, linv8, tmpw, &sh_ok);
             TRACE(t, 4);
             if (!ok && tid == 0) *a.fail = 1;
             // store L_jj (zero above the diagonal) and 1/diag
             for (int idx = tid; idx < TB * TB; idx += CT) {
                 const int r = idx >> 6, c = idx & 63;
-                a.H[(size_t)(i0 + r) * ld + j0 + c] = (c <= r) ? Ct[r * DL + c] : 0.0;
+                a.H[(size_t)(i0 + r) * ld + j0 + c] = (c <= r) ? As[r * RS + c] : 0.0;
             }
             if (tid < TB) a.dinv[j0 + tid] = dinv[tid];
         } else {
             if (MINB == 1 && i == j + 1) {  // park the pre-solve tile in the upper triangle for the next diagonal tile
                 for (int idx = tid; idx < TB * TB; idx += CT) {
                     const int r = idx >> 6, c = idx & 63;
-                    a.H[(size_t)(j0 + r) * ld + i0 + c] = Ct[r * DL + c];
+                    a.H[(size_t)(j0 + r) * ld + i0 + c] = As[r * RS + c];
                 }
                 publish_flag(a.preflags + j, a.epoch);
             }
             wait_flag(a.flags + (size_t)j * T + j, a.epoch);
-            load_tile_T(As, a.H + (size_t)j0 * ld + j0, ld);  // As[c][q] = L_jj[q][c]
+            load_tile_R(Bs, a.H + (size_t)j0 * ld + j0, ld);  // L_jj, row-major
             if (tid < TB) dinv[tid] = __ldcg(a.dinv + j0 + tid);
             __syncthreads();
             TRACE(t, 3);
-            tile_trsm(Ct, As, dinv);
+            tile_trsm_mma(As, Bs, dinv, linv8, tmpw);
             TRACE(t, 4);
             for (int idx = tid; idx < TB * TB; idx += CT) {
                 const int r = idx >> 6, c = idx & 63;
-                a.H[(size_t)(i0 + r) * ld + j0 + c] = Ct[r * DL + c];
+                a.H[(size_t)(i0 + r) * ld + j0 + c] = As[r * RS + c];
             }
         }
         TRACE(t, 5);
@@ -742,7 +849,7 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     a.epoch = 1;
     a.dx = dx;
     a.dinv = dinv;
-    const size_t sm = (size_t)(2 * TB * RS + 2 * TB + 32 * 34 + TB * DL) * sizeof(double);
+    const size_t sm = (size_t)(2 * TB * RS + 2 * TB + 32 * 34 + TB * DL + 8 * 96 + 8 * 160) * sizeof(double);
     err = cudaFuncSetAttribute(chol_factor_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (err != cudaSuccess) return err;
     err = cudaFuncSetAttribute(chol_factor_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -753,9 +860,9 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     const int total = T * (T + 1) / 2 + T;
     // small systems are latency-bound: one CTA per SM gives the critical-path tiles a whole fp64 pipe;
     // large ones are throughput-bound: two CTAs per SM overlap tile loads with the tile GEMMs
-    const int ctas = (T >= 40 ? 2 : 1) * sms;
+    const int ctas = (T >= 400 ? 2 : 1) * sms;
     const int grid = total < ctas ? total : ctas;
-    if (T >= 40) chol_factor_kernel<2><<<grid, CT, sm, st>>>(a);
+    if (T >= 400) chol_factor_kernel<2><<<grid, CT, sm, st>>>(a);
     else chol_factor_kernel<1><<<grid, CT, sm, st>>>(a);
     const size_t smb = (size_t)(2 * TB * (TB + 1) + 6 * TB) * sizeof(double);
     err = cudaFuncSetAttribute(chol_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);

@@ -208,6 +208,22 @@ __device__ __forceinline__ bool warp_potrf32(double (&a)[32], double *colbuf, in
     return ok;
 }
 
+// One copy of the unrolled register kernel in the binary: the second call on a tile then runs out of a warm
+// instruction cache (straight-line code executed once costs ~3 clk per instruction in fetch).  Called by one warp;
+// factorises the 32x32 block at Dblk (row stride RS) in place and writes 1/diag.
+__device__ __noinline__ bool warp_potrf32_smem(double *Dblk, double *dinv_out, double *colbuf) {
+    const int lane = threadIdx.x & 31;
+    double a[32];
+#pragma unroll
+    for (int c = 0; c < 32; c++) a[c] = Dblk[lane * RS + c];
+    double my_inv;
+    const bool ok = warp_potrf32(a, colbuf, lane, my_inv);
+#pragma unroll
+    for (int c = 0; c < 32; c++) Dblk[lane * RS + c] = a[c];
+    dinv_out[lane] = my_inv;
+    return ok;
+}
+
 // Warp-level X = A L^-T for a 32x32 block: lane r holds row r of A in registers; L (lower) is read from shared
 // memory TRANSPOSED, Lt[c * ldt + q] = L[q][c] (so that vectorised broadcast loads pair up independent updates),
 // dinv[c] = 1 / L[c][c].
@@ -228,15 +244,8 @@ __device__ __noinline__ void tile_trsm_mma(double *X, const double *L, const dou
 // L21 = A21 L11^-T (DMMA) -> A22 -= L21 L21^T (DMMA) -> potrf32.  All threads must call.
 __device__ bool tile_potrf_mma(double *D, double *dinv, double *colbuf, double *linv8, double *tmp, int *sh_ok) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double a[32];
     if (warp == 0) {
-#pragma unroll
-        for (int c = 0; c < 32; c++) a[c] = D[lane * RS + c];
-        double my_inv;
-        const bool ok = warp_potrf32(a, colbuf, lane, my_inv);
-#pragma unroll
-        for (int c = 0; c < 32; c++) D[lane * RS + c] = a[c];
-        dinv[lane] = my_inv;
+        const bool ok = warp_potrf32_smem(D, dinv, colbuf);
         if (!ok && lane == 0) *sh_ok = 0;
     }
     __syncthreads();
@@ -264,13 +273,7 @@ __device__ bool tile_potrf_mma(double *D, double *dinv, double *colbuf, double *
     }
     __syncthreads();
     if (warp == 0) {
-#pragma unroll
-        for (int c = 0; c < 32; c++) a[c] = D[(32 + lane) * RS + 32 + c];
-        double my_inv;
-        const bool ok = warp_potrf32(a, colbuf, lane, my_inv);
-#pragma unroll
-        for (int c = 0; c < 32; c++) D[(32 + lane) * RS + 32 + c] = a[c];
-        dinv[32 + lane] = my_inv;
+        const bool ok = warp_potrf32_smem(D + 32 * RS + 32, dinv + 32, colbuf);
         if (!ok && lane == 0) *sh_ok = 0;
     }
     __syncthreads();

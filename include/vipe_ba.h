@@ -120,6 +120,24 @@ int vipe_ba_profile_read(const vipe_ba_plan *plan, float ms_out[4], int *iterati
 /* Number of kernels the last vipe_ba_run / linearize+solve_update pair enqueued (for bench.py's gpu_launches). */
 int64_t vipe_ba_launch_count(const vipe_ba_plan *plan);
 
+/*
+ * The other operators of the reference's slam_ext module (csrc/slam_ext/slam.cpp:33-36), same layouts and semantics
+ * as their *_cuda hosts (geom_kernels.cu:1406-1507).  Index arrays are DEVICE int64; all work is enqueued on `stream`.
+ */
+/* projmap_cuda (:1436-1460): coords DEV [E,ht,wd,3] (third channel 0), valid DEV [E,ht,wd,1]. */
+int vipe_projmap(const float *poses, const float *disps, const float *intrinsics /*[4]*/, const int64_t *ii,
+                 const int64_t *jj, int64_t n_edges, int ht, int wd, float *coords, float *valid, void *stream);
+/* frame_distance_cuda (:1406-1434): intrinsics DEV [Q,4]; pi,pj pose ids, qi,qj intrinsics ids, di disparity ids; dist DEV [M]. */
+int vipe_frame_distance(const float *poses, const float *disps, const float *intrinsics, const int64_t *pi,
+                        const int64_t *pj, const int64_t *qi, const int64_t *qj, const int64_t *di, int64_t n_pairs, int ht,
+                        int wd, float beta, float *dist, void *stream);
+/* depth_filter_cuda (:1462-1486): counter DEV [n_ix,ht,wd]; neighbours ix-3..ix+3 inside [0, n_frames). */
+int vipe_depth_filter(const float *poses, const float *disps, const float *intrinsics /*[4]*/, const int64_t *ix,
+                      const float *thresh, int64_t n_ix, int64_t n_frames, int ht, int wd, float *counter, void *stream);
+/* iproj_cuda (:1488-1507): points DEV [N,ht,wd,3]. */
+int vipe_iproj(const float *poses, const float *disps, const float *intrinsics /*[4]*/, int64_t n_frames, int ht, int wd,
+               float *points, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 def test_library_exports_every_declared_symbol(lib_built):
     header = (ROOT / "include" / "vipe_ba.h").read_text()
-    declared = set(re.findall(r"\b(vipe_ba_[a-z_0-9]+)\s*\(", header))
+    declared = set(re.findall(r"\b(vipe_[a-z_0-9]+)\s*\(", header))
     assert len(declared) >= 20
     L = ctypes.CDLL(str(lib_built))
     for name in declared:

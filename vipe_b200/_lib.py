@@ -54,6 +54,10 @@ SIGNATURES = {
     "vipe_ba_debug_qw": (C.c_void_p, [C.c_void_p, C.c_void_p]),
     "vipe_ba_launch_count": (C.c_int64, [C.c_void_p]),
     "vipe_ba_set_graphs": (C.c_int, [C.c_void_p, C.c_int]),
+    "vipe_projmap": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vipe_frame_distance": (C.c_int, [C.c_void_p] * 8 + [C.c_int64, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "vipe_depth_filter": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "vipe_iproj": (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "vipe_ba_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "vipe_ba_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float * 4), C.POINTER(C.c_int)]),
 }

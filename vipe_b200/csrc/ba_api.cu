@@ -17,6 +17,9 @@ static int fail(const std::string &msg) {
     g_err = msg;
     return 1;
 }
+namespace vba {
+int set_last_error(const char *msg) { return fail(msg ? msg : "unknown error"); }
+}  // namespace vba
 #define VBA_CUDA(expr)                                                                          \
     do {                                                                                        \
         cudaError_t _e = (expr);                                                                \

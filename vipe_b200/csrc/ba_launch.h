@@ -32,4 +32,7 @@ cudaError_t launch_system_clear(double *H, double *b, int n, int npad, cudaStrea
 
 constexpr int kCholBlock = 64;
 
+// records msg as the calling thread's last error (vipe_ba_last_error) and returns 1
+int set_last_error(const char *msg);
+
 }  // namespace vba

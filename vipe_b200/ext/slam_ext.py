@@ -16,7 +16,7 @@ import torch
 from .. import _lib
 from ..plan import BAPlan, cached_plan
 
-__all__ = ["ba", "ba_plan"]
+__all__ = ["ba", "ba_plan", "projmap", "frame_distance", "depth_filter", "iproj"]
 
 
 def _check_contiguous(**tensors):
@@ -112,3 +112,76 @@ def ba(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, 
         _lib.check(_lib.lib().vipe_ba_run(plan.handle, C.byref(tens), ws.data_ptr(), iterations, float(lm), float(ep),
                                           int(motion_only), stream), "vipe_ba_run")
     return [dx, dz if dz is not None else torch.empty(0, device=dev)]
+
+
+# ------------------------------------------------------------------------------------------------
+# the other operators of the module (csrc/slam_ext/slam.cpp:33-36)
+def _common(poses, disps, intrinsics):
+    _check_contiguous(poses=poses, disps=disps, intrinsics=intrinsics)
+    _check_dtype(torch.float32, poses=poses, disps=disps, intrinsics=intrinsics)
+    if poses.device.type != "cuda":
+        raise RuntimeError("slam_ext ops need CUDA tensors (vipe_b200 has no CPU fallback)")
+    if disps.dim() != 3:
+        raise RuntimeError("disps must be [N,ht,wd]")
+    return poses.device, disps.shape[0], disps.shape[1], disps.shape[2]
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def projmap(poses, disps, intrinsics, ii, jj):
+    """Reprojected pixel coordinates and validity per edge; `projmap_cuda`, geom_kernels.cu:1436-1460.
+    Returns [coords[E,ht,wd,3] (third channel zero), valid[E,ht,wd,1]]."""
+    dev, N, ht, wd = _common(poses, disps, intrinsics)
+    _check_contiguous(ii=ii, jj=jj)
+    _check_dtype(torch.int64, ii=ii, jj=jj)
+    E = ii.numel()
+    coords = torch.empty(E, ht, wd, 3, dtype=torch.float32, device=dev)
+    valid = torch.empty(E, ht, wd, 1, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().vipe_projmap(poses.data_ptr(), disps.data_ptr(), intrinsics.data_ptr(), ii.data_ptr(),
+                                           jj.data_ptr(), E, ht, wd, coords.data_ptr(), valid.data_ptr(), _stream(dev)),
+                   "vipe_projmap")
+    return [coords, valid]
+
+
+def frame_distance(poses, disps, intrinsics, pi, pj, qi, qj, di, beta):
+    """Mean induced flow per frame pair; `frame_distance_cuda`, geom_kernels.cu:1406-1434 (intrinsics is [Q,4])."""
+    dev, N, ht, wd = _common(poses, disps, intrinsics)
+    _check_contiguous(pi=pi, pj=pj, qi=qi, qj=qj, di=di)
+    _check_dtype(torch.int64, pi=pi, pj=pj, qi=qi, qj=qj, di=di)
+    if intrinsics.dim() != 2 or intrinsics.shape[1] != 4:
+        raise RuntimeError("intrinsics must be [Q,4]")
+    M = pi.numel()
+    dist = torch.zeros(M, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().vipe_frame_distance(poses.data_ptr(), disps.data_ptr(), intrinsics.data_ptr(), pi.data_ptr(),
+                                                  pj.data_ptr(), qi.data_ptr(), qj.data_ptr(), di.data_ptr(), M, ht, wd,
+                                                  float(beta), dist.data_ptr(), _stream(dev)), "vipe_frame_distance")
+    return dist
+
+
+def depth_filter(poses, disps, intrinsics, ix, thresh):
+    """Multi-view depth-consistency count; `depth_filter_cuda`, geom_kernels.cu:1462-1486.  Returns counter[num,ht,wd]."""
+    dev, N, ht, wd = _common(poses, disps, intrinsics)
+    _check_contiguous(ix=ix, thresh=thresh)
+    _check_dtype(torch.int64, ix=ix)
+    _check_dtype(torch.float32, thresh=thresh)
+    num = ix.numel()
+    counter = torch.zeros(num, ht, wd, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().vipe_depth_filter(poses.data_ptr(), disps.data_ptr(), intrinsics.data_ptr(), ix.data_ptr(),
+                                                thresh.data_ptr(), num, N, ht, wd, counter.data_ptr(), _stream(dev)),
+                   "vipe_depth_filter")
+    return counter
+
+
+def iproj(poses, disps, intrinsics):
+    """Back-projection with the frame's own pose; `iproj_cuda`, geom_kernels.cu:1488-1507.  Returns points[N,ht,wd,3]."""
+    dev, N, ht, wd = _common(poses, disps, intrinsics)
+    points = torch.empty(N, ht, wd, 3, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().vipe_iproj(poses.data_ptr(), disps.data_ptr(), intrinsics.data_ptr(), N, ht, wd,
+                                         points.data_ptr(), _stream(dev)), "vipe_iproj")
+    return points

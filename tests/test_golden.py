@@ -37,3 +37,28 @@ def test_oracle_reproduces_reference_outputs(name, motion_only):
     if not motion_only:
         gdz = torch.from_numpy(g["dz_sub"]).double()
         assert (dz[:, ::STRIDE] - gdz).norm() <= 1e-2 * gdz.norm()
+
+
+def test_geom_oracle_reproduces_reference_outputs():
+    """projmap / frame_distance / depth_filter / iproj: CPU oracle vs vectors recorded from the reference's CUDA run."""
+    f = GOLD / "ref_geom_c2.npz"
+    if not f.is_file():
+        pytest.skip(f"{f.name} not recorded yet")
+    from oracle import geom_oracle as G
+
+    g = np.load(f)
+    pr = make_problem("c2")
+    coords, valid, z = G.projmap(pr.poses, pr.disps, pr.intrinsics, pr.ii, pr.jj)
+    assert (coords.view(120, -1, 3)[:, ::STRIDE] - torch.from_numpy(g["coords_sub"]).double()).abs().max() < 2e-3
+    assert (valid.view(120, -1)[:, ::STRIDE] != torch.from_numpy(g["valid_sub"]).double()).float().mean() < 1e-4
+    K2 = torch.stack([pr.intrinsics, pr.intrinsics * 1.01])
+    pi, pj, qi, qj = [torch.from_numpy(g[k]) for k in ("pi", "pj", "qi", "qj")]
+    dist, ratio = G.frame_distance(pr.poses, pr.disps, K2, pi, pj, qi, qj, pi, 0.3)
+    clear = (ratio - 0.75).abs() > 1e-3
+    assert torch.allclose(dist[clear], torch.from_numpy(g["dist"]).double()[clear], rtol=2e-4, atol=1e-4)
+    counter, margin = G.depth_filter(pr.poses_gt, pr.disps_gt, pr.intrinsics, torch.from_numpy(g["ix"]), torch.from_numpy(g["thresh"]))
+    c, m = counter.view(6, -1)[:, ::STRIDE], margin.view(6, -1)[:, ::STRIDE]
+    ok = m > 1e-4
+    assert torch.equal(c[ok], torch.from_numpy(g["counter_sub"]).double()[ok])
+    pts = G.iproj(pr.poses, pr.disps, pr.intrinsics)
+    assert torch.allclose(pts.view(16, -1, 3)[:, ::STRIDE], torch.from_numpy(g["points_sub"]).double(), rtol=2e-5, atol=1e-5)

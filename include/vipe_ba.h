@@ -89,6 +89,30 @@ typedef struct vipe_ba_tensors {
 int vipe_ba_run(const vipe_ba_plan *plan, const vipe_ba_tensors *t, void *workspace, int iterations, float lm,
                 float ep, int motion_only, void *stream);
 
+/*
+ * Semantic switches.  The defaults reproduce the reference's CUDA BA exactly as shipped
+ * (csrc/slam_ext/geom_kernels.cu); the other settings express the conventions of the Python BA that vipe/slam
+ * actually runs (GraphBuffer.bundle_adjustment, vipe/slam/components/buffer.py:373-525; SURVEY.md section 8(a')) so that
+ * an adapter can serve those callers with this operator.  vipe_ba_options_default fills the defaults.
+ */
+typedef struct vipe_ba_options {
+    float min_depth;     /* 0.25 (geom_kernels.cu:33);  Python path: 0.1 (vipe/utils/cameras.py:48) */
+    int depth_strict;    /* 0: invalid iff z < min_depth (:301);  1: valid iff z > min_depth (vipe/slam/maths/geom.py:263) */
+    float alpha;         /* 0.05 (:1359);  Python path: ba.dense_disp_alpha */
+    int sensor_mode;     /* 0: per-pixel mask disps_sens > 0, C += m*alpha + (1-m)*eta (:1361-1369)
+                            1: per-frame gate (frame_flags bit 0), prior on every pixel, damping everywhere
+                               (vipe/slam/ba/terms.py:244-300, buffer.py:470-489) */
+    float eta_scale;     /* disparity damping = eta_scale*eta + eta_bias;  1, 0  (Python path: 0.2, 2e-7) */
+    float eta_bias;
+    float dz_max;        /* dz > dz_max -> 0;  +inf  (Python path: 10, vipe/slam/maths/retractor.py:41) */
+    int renorm_quat;     /* 0 (Q6);  1: renormalise after the pose retraction like lietorch (so3.h:36-38) */
+    int damp_on_pose_hessian; /* 0: lm scales diag(A - S) (:1176);  1: lm scales diag(A) before the Schur complement (solver.py:161-164) */
+    int backsub_all_poses;    /* 0: pose index 0 never reaches dz (:1089, Q4);  1: every free pose does (solver.py:182) */
+    const unsigned char *frame_flags; /* DEV [K] or NULL.  bit 0: sensor gate (mode 1); bit 1: disparity of this kx frame fixed */
+} vipe_ba_options;
+void vipe_ba_options_default(vipe_ba_options *opt);
+int vipe_ba_set_options(vipe_ba_plan *plan, const vipe_ba_options *opt);
+
 /* CUDA-graph replay of repeated vipe_ba_run calls with identical arguments (default on). */
 int vipe_ba_set_graphs(vipe_ba_plan *plan, int on);
 
@@ -102,7 +126,8 @@ int vipe_ba_linearize(const vipe_ba_plan *plan, const vipe_ba_tensors *t, void *
                       void *stream);
 int vipe_ba_solve_update(const vipe_ba_plan *plan, const vipe_ba_tensors *t, void *workspace, float lm, float ep,
                          int motion_only, void *stream);
-/* DEV fp64 buffer holding [H (n x n, row-major, lower triangle valid) ; b (n)], n = 6*(t1-t0). */
+/* DEV fp64 buffer holding [H (n x n, row-major, lower triangle valid) ; b (n) ; diag of the pose Hessian (n)],
+   n = 6*(t1-t0) rounded up to 64; count_out = n*n + 2n.  This is what a sharded run all-reduces. */
 void *vipe_ba_system_buffer(const vipe_ba_plan *plan, void *workspace, int64_t *n_out, int64_t *count_out);
 
 /* Test hooks: DEV fp32 [K,HW] buffers written by the last linearize (Q = 1/C and Q*w of geom_kernels.cu:1365-1370). */

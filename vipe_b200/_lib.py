@@ -9,7 +9,7 @@ from pathlib import Path
 _SO = Path(__file__).resolve().parent / "lib" / "libvipe_ba.so"
 _lib = None
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class Tensors(C.Structure):
@@ -25,6 +25,24 @@ class Tensors(C.Structure):
         ("eta", C.c_void_p),
         ("dx_out", C.c_void_p),
         ("dz_out", C.c_void_p),
+    ]
+
+
+class Options(C.Structure):
+    """struct vipe_ba_options"""
+
+    _fields_ = [
+        ("min_depth", C.c_float),
+        ("depth_strict", C.c_int),
+        ("alpha", C.c_float),
+        ("sensor_mode", C.c_int),
+        ("eta_scale", C.c_float),
+        ("eta_bias", C.c_float),
+        ("dz_max", C.c_float),
+        ("renorm_quat", C.c_int),
+        ("damp_on_pose_hessian", C.c_int),
+        ("backsub_all_poses", C.c_int),
+        ("frame_flags", C.c_void_p),
     ]
 
 
@@ -54,6 +72,8 @@ SIGNATURES = {
     "vipe_ba_debug_qw": (C.c_void_p, [C.c_void_p, C.c_void_p]),
     "vipe_ba_launch_count": (C.c_int64, [C.c_void_p]),
     "vipe_ba_set_graphs": (C.c_int, [C.c_void_p, C.c_int]),
+    "vipe_ba_options_default": (None, [C.POINTER(Options)]),
+    "vipe_ba_set_options": (C.c_int, [C.c_void_p, C.POINTER(Options)]),
     "vipe_projmap": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vipe_frame_distance": (C.c_int, [C.c_void_p] * 8 + [C.c_int64, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "vipe_depth_filter": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

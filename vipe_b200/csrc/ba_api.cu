@@ -62,6 +62,7 @@ struct vipe_ba_plan {
     mutable std::vector<GraphEntry> graphs;
     mutable cudaStream_t capture_stream = nullptr;
     mutable bool use_graphs = true;
+    Options opt;  // semantic switches (vipe_ba_set_options)
     // optional stage timing
     bool profile = false;
     mutable std::vector<cudaEvent_t> events;  // 5 per iteration
@@ -75,7 +76,45 @@ struct vipe_ba_plan {
 };
 static constexpr int kMaxProfIters = 64;
 
-extern "C" int vipe_ba_abi_version(void) { return 1; }
+extern "C" int vipe_ba_abi_version(void) { return 2; }
+
+extern "C" void vipe_ba_options_default(vipe_ba_options *o) {
+    if (!o) return;
+    const Options d;
+    o->min_depth = d.min_depth;
+    o->depth_strict = d.depth_strict;
+    o->alpha = d.alpha;
+    o->sensor_mode = d.sensor_mode;
+    o->eta_scale = d.eta_scale;
+    o->eta_bias = d.eta_bias;
+    o->dz_max = d.dz_max;
+    o->renorm_quat = d.renorm_quat;
+    o->damp_on_pose_hessian = d.damp_on_pose_hessian;
+    o->backsub_all_poses = d.backsub_all_poses;
+    o->frame_flags = nullptr;
+}
+
+extern "C" int vipe_ba_set_options(vipe_ba_plan *p, const vipe_ba_options *o) {
+    if (!p || !o) return fail("null argument");
+    Options n;
+    n.min_depth = o->min_depth;
+    n.depth_strict = o->depth_strict;
+    n.alpha = o->alpha;
+    n.sensor_mode = o->sensor_mode;
+    n.eta_scale = o->eta_scale;
+    n.eta_bias = o->eta_bias;
+    n.dz_max = o->dz_max;
+    n.renorm_quat = o->renorm_quat;
+    n.damp_on_pose_hessian = o->damp_on_pose_hessian;
+    n.backsub_all_poses = o->backsub_all_poses;
+    n.frame_flags = o->frame_flags;
+    p->opt = n;
+    // captured graphs have the old options baked in
+    for (auto &g : p->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    p->graphs.clear();
+    return 0;
+}
 extern "C" const char *vipe_ba_last_error(void) { return g_err.c_str(); }
 
 extern "C" int vipe_ba_plan_create(const int64_t *ii, const int64_t *jj, int64_t n_edges, int64_t n_frames, int ht,
@@ -211,7 +250,7 @@ extern "C" int vipe_ba_plan_create(const int64_t *ii, const int64_t *jj, int64_t
     p->off_msc = take(sizeof(double) * (size_t)std::max<long long>(p->mbase[K], 1));
     p->off_q = take(sizeof(float) * (size_t)K * p->HW);
     p->off_qw = take(sizeof(float) * (size_t)K * p->HW);
-    p->off_sys = take(sizeof(double) * ((size_t)p->npad * p->npad + p->npad));
+    p->off_sys = take(sizeof(double) * ((size_t)p->npad * p->npad + 2 * (size_t)p->npad));  // [H ; b ; diag(A)]
     p->off_dx = take(sizeof(double) * (size_t)p->npad);  // 1/diag(L) of the factorisation
     p->off_flag = take(sizeof(int) * chol_scratch_ints(p->npad));
     p->flag_bytes = sizeof(int) * chol_scratch_ints(p->npad);
@@ -292,7 +331,7 @@ static Tables make_tables(const vipe_ba_plan *p, void *ws) {
 extern "C" void *vipe_ba_system_buffer(const vipe_ba_plan *p, void *ws, int64_t *n_out, int64_t *count_out) {
     if (!p || !ws) return nullptr;
     if (n_out) *n_out = p->npad;
-    if (count_out) *count_out = (int64_t)p->npad * p->npad + p->npad;
+    if (count_out) *count_out = (int64_t)p->npad * p->npad + 2 * (int64_t)p->npad;
     return (unsigned char *)ws + p->off_sys;
 }
 extern "C" float *vipe_ba_debug_q(const vipe_ba_plan *p, void *ws) { return (float *)((unsigned char *)ws + p->off_q); }
@@ -320,6 +359,7 @@ static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void 
 
     LinArgs la;
     la.tb = make_tables(p, ws);
+    la.opt = p->opt;
     la.poses = t->poses;
     la.disps = t->disps;
     la.intr = t->intrinsics;
@@ -346,6 +386,7 @@ static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void 
     ra.msc = (double *)(w + p->off_msc);
     ra.hsys = H;
     ra.bsys = b;
+    ra.adiag = b + p->npad;
     ra.n = p->npad;
     ra.motion_only = motion_only;
     VBA_CUDA(launch_frame_reduce(ra, nframes, std::max(p->dmax, 1), st));
@@ -369,13 +410,15 @@ static int solve_update_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, vo
     int *scratch = (int *)(w + p->off_flag);
     int cnt = 0;
     p->epoch++;
-    VBA_CUDA(launch_damped_solve(H, b, p->n, p->npad, lm, ep, t->dx_out, scratch, (double *)(w + p->off_dx), p->epoch, st, &cnt));
+    VBA_CUDA(launch_damped_solve(H, b, p->n, p->npad, lm, ep, t->dx_out, scratch, (double *)(w + p->off_dx),
+                                 p->opt.damp_on_pose_hessian ? b + p->npad : nullptr, p->epoch, st, &cnt));
     p->launches += cnt;
     if (mid) VBA_CUDA(cudaEventRecord(mid, st));
     const int nframes = p->k_hi - p->k_lo;
     if (!motion_only && nframes > 0) {
         BackArgs ba;
         ba.tb = make_tables(p, ws);
+        ba.opt = p->opt;
         ba.poses = t->poses;
         ba.intr = t->intrinsics;
         ba.weights = t->weights;
@@ -387,7 +430,7 @@ static int solve_update_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, vo
         VBA_CUDA(launch_backsub(ba, nframes, std::max(p->dmax, 1), st));
         p->launches++;
     }
-    VBA_CUDA(launch_pose_retr(t->poses, t->dx_out, p->t0, p->t1, st));
+    VBA_CUDA(launch_pose_retr(t->poses, t->dx_out, p->t0, p->t1, p->opt.renorm_quat, st));
     p->launches++;
     return 0;
 }

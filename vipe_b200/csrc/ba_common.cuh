@@ -26,8 +26,43 @@ struct Tables {
     int K, E, N, HW, wd, t0, t1, P, ntile, k_lo, k_hi;
 };
 
+// Semantic switches (defaults = the reference's CUDA BA; the other values serve the conventions of vipe/slam's Python BA,
+// SURVEY.md section 8(a')).  Mirrors vipe_ba_options in include/vipe_ba.h.
+struct Options {
+    float min_depth = kMinDepth;
+    int depth_strict = 0;   // 0: invalid iff z < min_depth (geom_kernels.cu:301); 1: valid iff z > min_depth (geom.py:263)
+    float alpha = kAlpha;
+    int sensor_mode = 0;    // 0: per-pixel mask (geom_kernels.cu:1361-1369); 1: per-frame gate, every pixel (terms.py:244-300)
+    float eta_scale = 1.0f, eta_bias = 0.0f;  // disparity damping = eta_scale * eta + eta_bias
+    float dz_max = 3.0e38f;  // dz > dz_max -> 0 (retractor.py:41)
+    int renorm_quat = 0;     // renormalise the quaternion after the pose retraction (lietorch so3.h:36-38)
+    int damp_on_pose_hessian = 0;  // 0: lm scales diag(A - S) (geom_kernels.cu:1176); 1: lm scales diag(A), the pose Hessian before
+                                   //    the Schur complement (solver.py:161-164)
+    int backsub_all_poses = 0;     // 0: EvT6x1 drops pose index 0 (geom_kernels.cu:1089, Q4); 1: every free pose reaches dz (solver.py:182)
+    const unsigned char *frame_flags = nullptr;  // DEV [K]: bit 0 sensor gate (mode 1), bit 1 disparity fixed
+};
+
+__device__ __forceinline__ bool depth_valid(float z, const Options &o) { return o.depth_strict ? (z > o.min_depth) : !(z < o.min_depth); }
+
+// disparity block of one pixel: C, w from the edge sums + prior/damping -> (Q, w)
+__device__ __forceinline__ void disparity_block(float Cacc, float Wacc, float h, float ds, float et, int flags, const Options &o,
+                                                float &Q, float &W) {
+    float C;
+    if (o.sensor_mode == 0) {
+        const bool mk = ds > 0.0f;
+        C = Cacc + (mk ? o.alpha : fmaf(o.eta_scale, et, o.eta_bias));
+        W = Wacc - (mk ? o.alpha * (h - ds) : 0.0f);
+    } else {
+        const bool gate = (flags & 1) != 0;
+        C = Cacc + fmaf(o.eta_scale, et, o.eta_bias) + (gate ? o.alpha : 0.0f);
+        W = Wacc - (gate ? o.alpha * (h - ds) : 0.0f);
+    }
+    Q = (flags & 2) ? 0.0f : __fdiv_rn(1.0f, C);  // a fixed disparity is eliminated with an infinite block: Q = 0
+}
+
 struct LinArgs {
     Tables tb;
+    Options opt;
     const float *poses, *disps, *intr, *dsens, *targets, *weights, *eta;
     float *epart;  // [E_slots][ntile][kEdgeStride]
     float *gpart;  // per frame: [ntile][npairs*36 + 6*d]
@@ -42,12 +77,14 @@ struct ReduceArgs {
     double *msc;   // M scratch
     double *hsys;  // [n*n] row-major, lower triangle (+ full diagonal blocks)
     double *bsys;  // [n]
+    double *adiag; // [n] diagonal of the pose Hessian A alone (before the Schur complement), for damp_on_pose_hessian
     int n;
     int motion_only;
 };
 
 struct BackArgs {
     Tables tb;
+    Options opt;
     const float *poses, *intr, *weights;
     float *disps;
     const float *qbuf, *qwbuf;

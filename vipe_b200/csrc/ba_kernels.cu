@@ -47,12 +47,12 @@ struct PixelGeom {
 };
 
 __device__ __forceinline__ PixelGeom pixel_geom(const float *__restrict__ ec, float xn, float yn, float h, float fx,
-                                                float fy) {
+                                                float fy, const Options &opt) {
     PixelGeom g;
     const float x = fmaf(ec[0], xn, fmaf(ec[1], yn, fmaf(h, ec[9], ec[2])));
     const float y = fmaf(ec[3], xn, fmaf(ec[4], yn, fmaf(h, ec[10], ec[5])));
     const float z = fmaf(ec[6], xn, fmaf(ec[7], yn, fmaf(h, ec[11], ec[8])));
-    g.valid = !(z < kMinDepth);
+    g.valid = depth_valid(z, opt);
     const float d = g.valid ? __frcp_rn(z) : 0.0f;
     g.dinv = d;
     g.X = x * d;
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(NT) linearize_kernel(const LinArgs a) {
         float us[6][PPT];
 #pragma unroll
         for (int s = 0; s < PPT; s++) {
-            const PixelGeom g = pixel_geom(c, xn[s], yn[s], h[s], fx, fy);
+            const PixelGeom g = pixel_geom(c, xn[s], yn[s], h[s], fx, fy, a.opt);
             float w_u = g.valid ? kWeightScale * wu[s] : 0.0f;  // :304-305
             float w_v = g.valid ? kWeightScale * wv[s] : 0.0f;
             const float ru = tu[s] - fmaf(fx, g.X, cx);  // :308-309
@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(NT) linearize_kernel(const LinArgs a) {
 
     if (!MOTION) {
         // disparity block: damping / sensor prior (:1359-1370), eliminate: Q = 1/C
+        const int fflags = a.opt.frame_flags ? a.opt.frame_flags[k] : 0;
         float qv[PPT], wv2[PPT], qw[PPT];
         if (inb) {
             float ds[PPT], et[PPT];
@@ -227,10 +228,8 @@ __global__ void __launch_bounds__(NT) linearize_kernel(const LinArgs a) {
             load_px<PPT>(a.eta + (size_t)k * HW + px0, et);
 #pragma unroll
             for (int s = 0; s < PPT; s++) {
-                const bool mk = ds[s] > 0.0f;
-                const float C = Cacc[s] + (mk ? kAlpha : et[s]);
-                const float W = Wacc[s] - (mk ? kAlpha * (h[s] - ds[s]) : 0.0f);
-                qv[s] = __fdiv_rn(1.0f, C);
+                float W;
+                disparity_block(Cacc[s], Wacc[s], h[s], ds[s], et[s], fflags, a.opt, qv[s], W);
                 wv2[s] = W;
                 qw[s] = qv[s] * W;
             }
@@ -400,6 +399,7 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
             const int hi = r >= c ? r : c, lo = r >= c ? c : r;
             const int sl = hslot(hi, lo);
             if (sl >= 0) v += hs[m * kEdgeVals + sl];
+            if (r == c && sl >= 0 && aj[m] >= 0) atomicAdd(a.adiag + 6 * aj[m] + r, hs[m * kEdgeVals + sl]);
         }
         msc[idx] = v;
         const int pa = aj[m], pb = aj[mp];
@@ -455,6 +455,19 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
             for (int q = 0; q < 6; q++) s += G[m * 36 + r * 6 + q] * gv[m * 6 + q];
         }
         atomicAdd(a.bsys + 6 * ai + r, s);
+    } else if (tid >= 96 && tid < 102) {
+        // diagonal of sum_m G_m H_jj,m G_m^T alone (the source pose's Hessian before the Schur complement)
+        const int r = tid - 96;
+        double s = 0.0;
+        for (int m = 0; m < d; m++) {
+            const double *Gm = G + m * 36 + r * 6;
+            for (int p = 0; p < 6; p++)
+                for (int q = 0; q < 6; q++) {
+                    const int sl = hslot(p >= q ? p : q, p >= q ? q : p);
+                    if (sl >= 0) s += Gm[p] * hs[m * kEdgeVals + sl] * Gm[q];
+                }
+        }
+        atomicAdd(a.adiag + 6 * ai + r, s);
     }
 }
 
@@ -486,7 +499,8 @@ __global__ void __launch_bounds__(NT) backsub_kernel(const BackArgs a) {
         float G[36];
         adjoint_G<float>(rp, G);
         const int ai = src - tb.t0, aj = j - tb.t0;
-        const bool vi = ai > 0 && ai < P, vj = aj > 0 && aj < P;  // Q4: index 0 is skipped on purpose
+        const int lo = a.opt.backsub_all_poses ? 0 : 1;  // Q4: the reference skips pose index 0 on purpose
+        const bool vi = ai >= lo && ai < P, vj = aj >= lo && aj < P;
         float y[6];
 #pragma unroll
         for (int c = 0; c < 6; c++) {
@@ -529,7 +543,7 @@ __global__ void __launch_bounds__(NT) backsub_kernel(const BackArgs a) {
         load_px<PPT>(a.weights + base + HW, wv);
 #pragma unroll
         for (int s = 0; s < PPT; s++) {
-            const PixelGeom g = pixel_geom(c, xn[s], yn[s], h[s], fx, fy);
+            const PixelGeom g = pixel_geom(c, xn[s], yn[s], h[s], fx, fy, a.opt);
             const float w_u = g.valid ? kWeightScale * wu[s] : 0.0f;
             const float w_v = g.valid ? kWeightScale * wv[s] : 0.0f;
             float u6[6];
@@ -544,6 +558,7 @@ __global__ void __launch_bounds__(NT) backsub_kernel(const BackArgs a) {
 #pragma unroll
     for (int s = 0; s < PPT; s++) {
         dz[s] = fmaf(-q[s], acc[s], qw[s]);
+        if (dz[s] > a.opt.dz_max) dz[s] = 0.0f;  // retractor.py:41 (off by default)
         hn[s] = h[s] + dz[s];
     }
     store_px<PPT>(a.disps + (size_t)src * HW + px0, hn);
@@ -553,7 +568,7 @@ __global__ void __launch_bounds__(NT) backsub_kernel(const BackArgs a) {
 // =================================================================================================
 // Stage 4b: pose retraction T <- exp(xi) T without quaternion renormalisation
 // (pose_retr_kernel / retrSE3 / expSE3 / expSO3, geom_kernels.cu:116-177,882-931).
-__global__ void pose_retr_kernel(float *__restrict__ poses, const float *__restrict__ dx, int t0, int t1) {
+__global__ void pose_retr_kernel(float *__restrict__ poses, const float *__restrict__ dx, int t0, int t1, int renorm) {
     const int kk = t0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (kk >= t1) return;
     float xi[6];
@@ -592,6 +607,11 @@ __global__ void pose_retr_kernel(float *__restrict__ poses, const float *__restr
     q1[1] = dq[3] * q[1] + dq[1] * q[3] + dq[2] * q[0] - dq[0] * q[2];
     q1[2] = dq[3] * q[2] + dq[2] * q[3] + dq[0] * q[1] - dq[1] * q[0];
     q1[3] = dq[3] * q[3] - dq[0] * q[0] - dq[1] * q[1] - dq[2] * q[2];
+    if (renorm) {  // lietorch's group product renormalises (so3.h:36-38); the reference CUDA BA does not (Q6)
+        const float inv = rsqrtf(q1[0] * q1[0] + q1[1] * q1[1] + q1[2] * q1[2] + q1[3] * q1[3]);
+#pragma unroll
+        for (int n = 0; n < 4; n++) q1[n] *= inv;
+    }
     // actSO3(dq, t) (:69-78)
     const float uv[3] = {2.0f * (dq[1] * t[2] - dq[2] * t[1]), 2.0f * (dq[2] * t[0] - dq[0] * t[2]), 2.0f * (dq[0] * t[1] - dq[1] * t[0])};
     float t1v[3];
@@ -683,10 +703,10 @@ cudaError_t launch_backsub(const BackArgs &a, int nframes, int dmax, cudaStream_
     return launch_back_t<128, 1>(a, nframes, dmax, st);
 }
 
-cudaError_t launch_pose_retr(float *poses, const float *dx, int t0, int t1, cudaStream_t st) {
+cudaError_t launch_pose_retr(float *poses, const float *dx, int t0, int t1, int renorm, cudaStream_t st) {
     const int P = t1 - t0;
     if (P <= 0) return cudaSuccess;
-    pose_retr_kernel<<<(P + 127) / 128, 128, 0, st>>>(poses, dx, t0, t1);
+    pose_retr_kernel<<<(P + 127) / 128, 128, 0, st>>>(poses, dx, t0, t1, renorm);
     return cudaGetLastError();
 }
 

@@ -16,7 +16,7 @@ bool tile_config2(int HW, int dmax, bool motion, int &NT);
 cudaError_t launch_linearize2(const LinArgs &a, int nframes, int dmax, bool motion, int NT, cudaStream_t st);
 cudaError_t launch_frame_reduce(const ReduceArgs &a, int nframes, int dmax, cudaStream_t st);
 cudaError_t launch_backsub(const BackArgs &a, int nframes, int dmax, cudaStream_t st);
-cudaError_t launch_pose_retr(float *poses, const float *dx, int t0, int t1, cudaStream_t st);
+cudaError_t launch_pose_retr(float *poses, const float *dx, int t0, int t1, int renorm, cudaStream_t st);
 
 // Dense damped Cholesky solve of the reduced camera system (chol.cu).
 //   H: [npad x npad] fp64 row-major, lower triangle valid on entry (destroyed);  b: [npad] fp64 (destroyed)
@@ -25,7 +25,8 @@ cudaError_t launch_pose_retr(float *poses, const float *dx, int t0, int t1, cuda
 // `scratch` is chol_scratch_ints(npad) ints of device memory, zeroed once when the workspace is set up; `epoch` must be
 // a value never used before on this scratch (tile ready flags are epoch-valued so they need no per-solve reset).
 cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx, int *scratch,
-                                double *dinv /*[npad]*/, int epoch, cudaStream_t st, int *launches);
+                                double *dinv /*[npad]*/, const double *dampdiag /*[npad] or null*/, int epoch, cudaStream_t st,
+                                int *launches);
 size_t chol_scratch_ints(int npad);
 // zero [H ; b] and put the identity on the padded diagonal
 cudaError_t launch_system_clear(double *H, double *b, int n, int npad, cudaStream_t st);

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(2 * NT) linearize2_kernel(const LinArgs a) {
         const float2 x = ffma2(c[0], xn, ffma2(c[1], yn, ffma2(h, t0, c[2])));
         const float2 y = ffma2(c[3], xn, ffma2(c[4], yn, ffma2(h, t1, c[5])));
         const float2 z = ffma2(c[6], xn, ffma2(c[7], yn, ffma2(h, t2, c[8])));
-        const bool v0 = !(z.x < kMinDepth) && inb, v1 = !(z.y < kMinDepth) && inb;  // :301
+        const bool v0 = depth_valid(z.x, a.opt) && inb, v1 = depth_valid(z.y, a.opt) && inb;  // :301
         // d = 1/z: MUFU seed + one Newton step (<= 1 ulp), forced to 0 where invalid
         float2 r = make_float2(rcp_approx(z.x), rcp_approx(z.y));
         r = ffma2(r, ffma2(neg2(z), r, splat(1.0f)), r);
@@ -223,11 +223,9 @@ __global__ void __launch_bounds__(2 * NT) linearize2_kernel(const LinArgs a) {
             if (inb) {
                 const float2 ds = __ldg(reinterpret_cast<const float2 *>(a.dsens + (size_t)src * HW + px0));
                 const float2 et = __ldg(reinterpret_cast<const float2 *>(a.eta + (size_t)k * HW + px0));
-                const bool m0 = ds.x > 0.0f, m1 = ds.y > 0.0f;
-                const float C0 = Cacc.x + (m0 ? kAlpha : et.x), C1 = Cacc.y + (m1 ? kAlpha : et.y);
-                wz.x = Wacc.x - (m0 ? kAlpha * (h.x - ds.x) : 0.0f);
-                wz.y = Wacc.y - (m1 ? kAlpha * (h.y - ds.y) : 0.0f);
-                qv = make_float2(__fdiv_rn(1.0f, C0), __fdiv_rn(1.0f, C1));
+                const int fflags = a.opt.frame_flags ? a.opt.frame_flags[k] : 0;
+                disparity_block(Cacc.x, Wacc.x, h.x, ds.x, et.x, fflags, a.opt, qv.x, wz.x);
+                disparity_block(Cacc.y, Wacc.y, h.y, ds.y, et.y, fflags, a.opt, qv.y, wz.y);
                 *reinterpret_cast<float2 *>(a.qbuf + (size_t)k * HW + px0) = qv;
                 *reinterpret_cast<float2 *>(a.qwbuf + (size_t)k * HW + px0) = make_float2(qv.x * wz.x, qv.y * wz.y);
             }

@@ -26,8 +26,8 @@ __global__ void pad_identity_kernel(double *H, int n, int npad) {
 }
 
 cudaError_t launch_system_clear(double *H, double *b, int n, int npad, cudaStream_t st) {
-    // H and b are contiguous ([npad*npad] then [npad])
-    cudaError_t err = cudaMemsetAsync(H, 0, ((size_t)npad * npad + npad) * sizeof(double), st);
+    // H, b and the pose-Hessian diagonal are contiguous ([npad*npad], [npad], [npad])
+    cudaError_t err = cudaMemsetAsync(H, 0, ((size_t)npad * npad + 2 * (size_t)npad) * sizeof(double), st);
     if (err != cudaSuccess) return err;
     (void)b;
     if (npad > n) {
@@ -92,6 +92,7 @@ struct CholArgs {
     int epoch;
     float *dx;
     double *dinv;  // [npad] 1 / diag(L)
+    const double *dampdiag;  // [npad] or null: lm scales this instead of the matrix's own diagonal
 };
 
 // Tile GEMM on the fp64 tensor cores (mma.sync.m8n8k4.f64 -> DMMA).  Measured on B200: DMMA issues at the full
@@ -535,8 +536,8 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
                 const double2 v = __ldcg(reinterpret_cast<const double2 *>(a.H + (size_t)(i0 + r) * ld + j0 + c));
                 acc[mt][0] = v.x, acc[mt][1] = v.y;
                 if (i == j && i0 + r < a.n) {
-                    if (r == c) acc[mt][0] += (double)a.ep + (double)a.lm * acc[mt][0];
-                    if (r == c + 1) acc[mt][1] += (double)a.ep + (double)a.lm * acc[mt][1];
+                    if (r == c) acc[mt][0] += (double)a.ep + (double)a.lm * (a.dampdiag ? a.dampdiag[i0 + r] : acc[mt][0]);
+                    if (r == c + 1) acc[mt][1] += (double)a.ep + (double)a.lm * (a.dampdiag ? a.dampdiag[i0 + r] : acc[mt][1]);
                 }
             }
         }
@@ -720,7 +721,8 @@ __device__ void smem_trsv_bwd(const double *L, const double *dinv, double *v, in
 }
 
 __global__ void __launch_bounds__(CT) chol_small_kernel(const double *__restrict__ H, const double *__restrict__ b, int n,
-                                                        int ld, int T, float lm, float ep, float *__restrict__ dx) {
+                                                        int ld, int T, float lm, float ep, float *__restrict__ dx,
+                                                        const double *__restrict__ dampdiag) {
     extern __shared__ __align__(16) double sm[];
     double *A00 = sm;                   // [64][DL]
     double *A10 = A00 + TB * DL;        // [64][DL]
@@ -737,12 +739,12 @@ __global__ void __launch_bounds__(CT) chol_small_kernel(const double *__restrict
     for (int idx = tid; idx < TB * TB; idx += CT) {
         const int r = idx >> 6, c = idx & 63;
         double v = (c <= r) ? H[(size_t)r * ld + c] : 0.0;
-        if (r == c && r < n) v += (double)ep + (double)lm * v;  // geom_kernels.cu:1176
+        if (r == c && r < n) v += (double)ep + (double)lm * (dampdiag ? dampdiag[r] : v);  // geom_kernels.cu:1176
         A00[r * DL + c] = v;
         if (T == 2) {
             A10[r * DL + c] = H[(size_t)(TB + r) * ld + c];
             double w = (c <= r) ? H[(size_t)(TB + r) * ld + TB + c] : 0.0;
-            if (r == c && TB + r < n) w += (double)ep + (double)lm * w;
+            if (r == c && TB + r < n) w += (double)ep + (double)lm * (dampdiag ? dampdiag[TB + r] : w);
             A11[r * DL + c] = w;
         }
     }
@@ -816,22 +818,22 @@ __global__ void __launch_bounds__(CT) chol_small_kernel(const double *__restrict
     for (int i = tid; i < n; i += CT) dx[i] = (float)rhs[i];
 }
 
-static cudaError_t launch_small_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx, cudaStream_t st,
-                                      int *launches) {
+static cudaError_t launch_small_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx,
+                                      const double *dampdiag, cudaStream_t st, int *launches) {
     const size_t sm = (size_t)(3 * TB * DL + TB * LD + 3 * TB + 32 * 34 + 2 * TB) * sizeof(double);
     cudaError_t err = cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (err != cudaSuccess) return err;
-    chol_small_kernel<<<1, CT, sm, st>>>(H, b, n, npad, npad / TB, lm, ep, dx);
+    chol_small_kernel<<<1, CT, sm, st>>>(H, b, n, npad, npad / TB, lm, ep, dx, dampdiag);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
 
 cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx, int *scratch,
-                                double *dinv, int epoch, cudaStream_t st, int *launches) {
+                                double *dinv, const double *dampdiag, int epoch, cudaStream_t st, int *launches) {
     // scratch (ints): [0..1] counters, [2] fail, [16 .. 16+T) xflags, [16+T .. 16+2T) preflags, then (T+1)*T tile flags
     const int T = npad / TB;
     (void)epoch;
-    if (T <= 2) return launch_small_solve(H, b, n, npad, lm, ep, dx, st, launches);
+    if (T <= 2) return launch_small_solve(H, b, n, npad, lm, ep, dx, dampdiag, st, launches);
     // ready flags, counters and the failure flag are reset by one small memset per solve (graph-capturable, and the
     // flags never carry state from one solve to the next)
     cudaError_t err = cudaMemsetAsync(scratch, 0, chol_scratch_ints(npad) * sizeof(int), st);
@@ -852,6 +854,7 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     a.epoch = 1;
     a.dx = dx;
     a.dinv = dinv;
+    a.dampdiag = dampdiag;
     const size_t sm = (size_t)(2 * TB * RS + 2 * TB + 32 * 34 + TB * DL + 8 * 96 + 8 * 160) * sizeof(double);
     err = cudaFuncSetAttribute(chol_factor_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (err != cudaSuccess) return err;

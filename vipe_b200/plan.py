@@ -85,6 +85,21 @@ class BAPlan:
     def workspace_bytes(self) -> int:
         return int(_lib.lib().vipe_ba_workspace_bytes(self._h))
 
+    def set_options(self, **kw):
+        """vipe_ba_set_options: override the reference-CUDA defaults (see include/vipe_ba.h).  `frame_flags` is a CUDA
+        uint8 tensor [K] that must stay alive as long as the plan uses it."""
+        opt = _lib.Options()
+        _lib.lib().vipe_ba_options_default(C.byref(opt))
+        self._flags_keepalive = kw.get("frame_flags")
+        for k, v in kw.items():
+            if k == "frame_flags":
+                opt.frame_flags = v.data_ptr() if v is not None else None
+            else:
+                if not hasattr(opt, k):
+                    raise TypeError(f"unknown BA option {k}")
+                setattr(opt, k, v)
+        _lib.check(_lib.lib().vipe_ba_set_options(self._h, C.byref(opt)), "vipe_ba_set_options")
+
     @property
     def launch_count(self) -> int:
         return int(_lib.lib().vipe_ba_launch_count(self._h))
@@ -103,7 +118,7 @@ class BAPlan:
         return ws
 
     def system_view(self, ws: torch.Tensor) -> torch.Tensor:
-        """fp64 view [npad*npad + npad] of the reduced camera system inside the workspace (all-reduce target)."""
+        """fp64 view [npad*npad + 2*npad] of the reduced camera system ([H ; b ; diag of the pose Hessian]) inside the workspace (all-reduce target)."""
         n, cnt = C.c_int64(), C.c_int64()
         ptr = _lib.lib().vipe_ba_system_buffer(self._h, ws.data_ptr(), C.byref(n), C.byref(cnt))
         off = ptr - ws.data_ptr()
@@ -122,11 +137,12 @@ _CACHE: "OrderedDict[tuple, BAPlan]" = OrderedDict()
 _CACHE_MAX = 8
 
 
-def cached_plan(ii_h: torch.Tensor, jj_h: torch.Tensor, n_frames, ht, wd, t0, t1, rank=0, world=1) -> BAPlan:
+def cached_plan(ii_h: torch.Tensor, jj_h: torch.Tensor, n_frames, ht, wd, t0, t1, rank=0, world=1, tag="") -> BAPlan:
     """Plans depend only on the graph, and SLAM calls BA many times on the same graph (every GRU step of
     FactorGraph.update / update_batch, vipe/slam/components/factor_graph.py:296,378), so keep a few."""
     dig = hashlib.blake2b(ii_h.numpy().tobytes() + b"|" + jj_h.numpy().tobytes(), digest_size=16).digest()
-    key = (dig, int(n_frames), int(ht), int(wd), int(t0), int(t1), rank, world)
+    # `tag` separates plans that carry different semantic options (vipe_ba_set_options is per plan)
+    key = (dig, int(n_frames), int(ht), int(wd), int(t0), int(t1), rank, world, tag)
     p = _CACHE.get(key)
     if p is None:
         p = BAPlan(ii_h, jj_h, n_frames, ht, wd, t0, t1, rank, world)

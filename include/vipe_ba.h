@@ -49,6 +49,18 @@ const char *vipe_ba_last_error(void);
  */
 int vipe_ba_plan_create(const int64_t *ii, const int64_t *jj, int64_t n_edges, int64_t n_frames, int ht, int wd,
                         int t0, int t1, int rank, int world, vipe_ba_plan **out);
+/*
+ * Batched plan: n_problems INDEPENDENT small problems in one set of launches (e.g. motion-only BA of many video clips,
+ * BASELINE config 5).  Frames, edges and tensors are concatenated; problem c owns frames
+ * [frame_ptr[c], frame_ptr[c+1]) and optimises the poses of its window [t0s[c], t1s[c]) (global frame ids); edges must
+ * stay inside one problem.  Each reduced system is solved by its own CTA, so 6*(t1-t0) <= 128 per problem.
+ * dx_out is [sum_c (t1-t0), 6] in problem order (vipe_ba_plan_num_free_poses rows).  The semantics of every problem are
+ * those of a separate slam_ext.ba call.
+ */
+int vipe_ba_plan_create_batch(const int64_t *ii, const int64_t *jj, int64_t n_edges, int64_t n_frames, int ht, int wd,
+                              int n_problems, const int64_t *frame_ptr, const int64_t *t0s, const int64_t *t1s,
+                              vipe_ba_plan **out);
+int64_t vipe_ba_plan_num_free_poses(const vipe_ba_plan *plan);
 void vipe_ba_plan_destroy(vipe_ba_plan *plan);
 
 /* K = |kx|, kx = sorted unique of cat(arange(t0,t1), ii)  (geom_kernels.cu:1305-1308). */

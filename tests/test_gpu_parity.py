@@ -251,3 +251,39 @@ def test_c4_two_iterations_vs_reference_run(slam_ext, dev):
     print("C4 vs reference run:", te, re_, de, float((dx - dxr).norm() / dxr.norm()), float((dz - dzr).norm() / dzr.norm()))
     assert te <= TOL_T and re_ <= TOL_R and de <= TOL_D, (te, re_, de)
     assert (dx - dxr).norm() <= 5e-2 * dxr.norm()
+
+
+@pytest.mark.parametrize("motion_only", [True, False])
+def test_batched_clips_match_per_clip_oracle(slam_ext, dev, motion_only):
+    """ba_batch: independent clips in one set of launches; every clip must equal its own oracle run (BASELINE config 5
+    is the motion-only case)."""
+    clips = [make_problem("c1", clip=c) for c in range(5)]
+    N, E = 8, 24
+    cat = lambda xs: torch.cat(xs, dim=0)
+    poses, disps = cat([p.poses for p in clips]), cat([p.disps for p in clips])
+    dsens = cat([p.disps_sens for p in clips])
+    targets, weights = cat([p.targets for p in clips]), cat([p.weights for p in clips])
+    eta = cat([p.eta for p in clips])  # every clip's kx is all 8 frames
+    ii = cat([p.ii + c * N for c, p in enumerate(clips)])
+    jj = cat([p.jj + c * N for c, p in enumerate(clips)])
+    frame_ptr = [c * N for c in range(6)]
+    t0s = [c * N + 1 for c in range(5)]
+    t1s = [(c + 1) * N for c in range(5)]
+    a = [x.to(dev) for x in (poses, disps, clips[0].intrinsics, dsens, targets, weights, eta, ii, jj)]
+    dx, dz = slam_ext.ba_batch(*a, frame_ptr, t0s, t1s, 2, 1e-4, 0.1, motion_only)
+    torch.cuda.synchronize()
+    assert dx.shape == (35, 6)
+    for c, p in enumerate(clips):
+        ref = p.args()
+        ref[14] = motion_only
+        tr = O.Trace()
+        dxr, dzr = O.ba(*ref, dtype=torch.float64, trace=tr)
+        pc = a[0][c * N:(c + 1) * N]
+        te, re_ = pose_errors(pc, ref[0], 1, N)
+        assert te <= TOL_T and re_ <= TOL_R, (c, te, re_)
+        assert torch.equal(pc[:1].cpu(), p.poses[:1])
+        if motion_only:
+            assert torch.equal(a[1][c * N:(c + 1) * N].cpu(), p.disps)
+        else:
+            assert disp_error(a[1][c * N:(c + 1) * N], ref[1], tr.bk.kx) <= TOL_D
+        assert (dx[c * 7:(c + 1) * 7].cpu().double() - dxr).norm() <= 2e-2 * dxr.norm() + 1e-7

@@ -52,6 +52,9 @@ SIGNATURES = {
     "vipe_ba_last_error": (C.c_char_p, []),
     "vipe_ba_plan_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "vipe_ba_plan_create_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "vipe_ba_plan_num_free_poses": (C.c_int64, [C.c_void_p]),
     "vipe_ba_plan_destroy": (None, [C.c_void_p]),
     "vipe_ba_plan_num_kx": (C.c_int64, [C.c_void_p]),
     "vipe_ba_plan_copy_kx": (C.c_int, [C.c_void_p, C.c_void_p]),

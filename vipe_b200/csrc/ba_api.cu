@@ -41,6 +41,13 @@ struct vipe_ba_plan {
     std::vector<int64_t> kx, kk_exp;
     std::vector<int> kx32, fptr, fedge, e_jj;
     std::vector<long long> gbase, mbase;
+    // problems (C == 1 unless created with vipe_ba_plan_create_batch)
+    int C = 1;
+    bool any_padding = false;
+    size_t sys_doubles = 0;
+    std::vector<int> pose_slot, pose_row, frame_prob, prob_npad, prob_n, prob_row0;
+    std::vector<long long> prob_hoff;
+    size_t off_pslot = 0, off_prow = 0, off_fprob = 0, off_phoff = 0, off_pnpad = 0, off_pn = 0, off_prow0 = 0;
     std::vector<int64_t> own_lo, own_hi;
     // workspace layout (byte offsets)
     size_t off_kx = 0, off_fptr = 0, off_fedge = 0, off_ejj = 0, off_gbase = 0, off_mbase = 0, idx_bytes = 0;
@@ -117,19 +124,33 @@ extern "C" int vipe_ba_set_options(vipe_ba_plan *p, const vipe_ba_options *o) {
 }
 extern "C" const char *vipe_ba_last_error(void) { return g_err.c_str(); }
 
-extern "C" int vipe_ba_plan_create(const int64_t *ii, const int64_t *jj, int64_t n_edges, int64_t n_frames, int ht,
-                                   int wd, int t0, int t1, int rank, int world, vipe_ba_plan **out) {
+// C independent problems share one plan: problem c owns frames [frame_ptr[c], frame_ptr[c+1]) and optimises the poses
+// of its window [t0s[c], t1s[c]) (global frame ids).  C == 1 is the reference operator.
+static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edges, int64_t n_frames, int ht, int wd, int C,
+                            const int64_t *frame_ptr, const int64_t *t0s, const int64_t *t1s, int rank, int world,
+                            vipe_ba_plan **out) {
     if (!out) return fail("out is null");
     *out = nullptr;
-    if (n_edges < 0 || n_frames <= 0 || ht <= 0 || wd <= 0) return fail("bad sizes");
-    if (t0 < 0 || t1 < t0 || t1 > n_frames) return fail("need 0 <= t0 <= t1 <= n_frames");
+    if (n_edges < 0 || n_frames <= 0 || ht <= 0 || wd <= 0 || C < 1) return fail("bad sizes");
     if (world < 1 || rank < 0 || rank >= world) return fail("bad rank/world");
+    if (C > 1 && world != 1) return fail("batched plans are not sharded: give every rank its own clips");
     if (n_edges > 0 && (!ii || !jj)) return fail("ii/jj null");
+    if (frame_ptr[0] != 0 || frame_ptr[C] != n_frames) return fail("frame_ptr must run from 0 to n_frames");
+    std::vector<int> prob_of_frame(n_frames, -1);
+    for (int c = 0; c < C; c++) {
+        if (frame_ptr[c + 1] < frame_ptr[c]) return fail("frame_ptr must be non-decreasing");
+        if (t0s[c] < frame_ptr[c] || t1s[c] < t0s[c] || t1s[c] > frame_ptr[c + 1])
+            return fail("need frame_ptr[c] <= t0 <= t1 <= frame_ptr[c+1] for every problem");
+        for (int64_t f = frame_ptr[c]; f < frame_ptr[c + 1]; f++) prob_of_frame[f] = c;
+    }
     for (int64_t e = 0; e < n_edges; e++) {
         if (ii[e] < 0 || ii[e] >= n_frames || jj[e] < 0 || jj[e] >= n_frames)
             return fail("edge " + std::to_string(e) + " references a frame outside [0, n_frames)");
+        if (prob_of_frame[ii[e]] != prob_of_frame[jj[e]]) return fail("edge " + std::to_string(e) + " connects two different problems");
     }
+    const int t0 = (int)t0s[0], t1 = (int)t1s[0];
     auto *p = new vipe_ba_plan();
+    p->C = C;
     p->E = n_edges;
     p->N = n_frames;
     p->ht = ht;
@@ -137,17 +158,48 @@ extern "C" int vipe_ba_plan_create(const int64_t *ii, const int64_t *jj, int64_t
     p->HW = ht * wd;
     p->t0 = t0;
     p->t1 = t1;
-    p->P = t1 - t0;
     p->rank = rank;
     p->world = world;
-    p->n = 6 * p->P;
-    p->npad = std::max(kCholBlock, (p->n + kCholBlock - 1) / kCholBlock * kCholBlock);
+    // per-problem reduced systems
+    p->pose_slot.assign(n_frames, -1);
+    p->pose_row.assign(n_frames, -1);
+    p->prob_n.resize(C);
+    p->prob_npad.resize(C);
+    p->prob_row0.resize(C);
+    p->prob_hoff.resize(C);
+    {
+        int row = 0;
+        long long hoff = 0;
+        for (int c = 0; c < C; c++) {
+            const int Pc = (int)(t1s[c] - t0s[c]);
+            p->prob_row0[c] = row;
+            p->prob_n[c] = 6 * Pc;
+            p->prob_npad[c] = std::max(kCholBlock, (6 * Pc + kCholBlock - 1) / kCholBlock * kCholBlock);
+            p->prob_hoff[c] = hoff;
+            if (p->prob_npad[c] > p->prob_n[c]) p->any_padding = true;
+            if (C > 1 && p->prob_npad[c] > 2 * kCholBlock) {
+                delete p;
+                return fail("batched plans need small problems: 6 * (t1 - t0) <= 128 per problem");
+            }
+            hoff += (long long)p->prob_npad[c] * p->prob_npad[c] + 2LL * p->prob_npad[c];
+            for (int64_t f = t0s[c]; f < t1s[c]; f++) {
+                p->pose_slot[f] = (int)(f - t0s[c]);
+                p->pose_row[f] = row + (int)(f - t0s[c]);
+            }
+            row += Pc;
+        }
+        p->P = row;
+        p->sys_doubles = (size_t)hoff;
+    }
+    p->n = p->prob_n[0];
+    p->npad = p->prob_npad[0];
     const int P = p->P;
     const int64_t E = n_edges;
 
     // kx = sorted unique of cat(arange(t0,t1), ii);  kk_exp = inverse   (geom_kernels.cu:1301-1308)
     std::vector<char> present(n_frames, 0);
-    for (int t = t0; t < t1; t++) present[t] = 1;
+    for (int c = 0; c < C; c++)
+        for (int64_t t = t0s[c]; t < t1s[c]; t++) present[t] = 1;
     for (int64_t e = 0; e < E; e++) present[ii[e]] = 1;
     std::vector<int> slot(n_frames, -1);
     for (int64_t f = 0; f < n_frames; f++)
@@ -157,8 +209,11 @@ extern "C" int vipe_ba_plan_create(const int64_t *ii, const int64_t *jj, int64_t
         }
     p->K = (int)p->kx.size();
     p->kk_exp.resize(P + E);
-    for (int t = 0; t < P; t++) p->kk_exp[t] = slot[t0 + t];
+    for (int64_t f = 0; f < n_frames; f++)
+        if (p->pose_row[f] >= 0) p->kk_exp[p->pose_row[f]] = slot[f];
     for (int64_t e = 0; e < E; e++) p->kk_exp[P + e] = slot[ii[e]];
+    p->frame_prob.resize(p->K);
+    for (int k = 0; k < p->K; k++) p->frame_prob[k] = prob_of_frame[p->kx[k]];
 
     // CSR of edges by source frame, ascending edge id inside a frame (accum_cuda's ptrs/idxs, :946-981)
     const int K = p->K;
@@ -179,10 +234,10 @@ extern "C" int vipe_ba_plan_create(const int64_t *ii, const int64_t *jj, int64_t
     for (int k = 0; k < K; k++) {
         int64_t rows = 0;
         const int f = (int)p->kx[k];
-        if (f >= t0 && f < t1) rows++;  // the Ei row of pose f
+        if (p->pose_slot[f] >= 0) rows++;  // the Ei row of pose f
         for (int s = p->fptr[k]; s < p->fptr[k + 1]; s++) {
             const int j = p->e_jj[p->fedge[s]];
-            if (j >= t0 && j < t1) rows++;
+            if (p->pose_slot[j] >= 0) rows++;
         }
         p->n_triples += rows * rows;
     }
@@ -244,14 +299,21 @@ extern "C" int vipe_ba_plan_create(const int64_t *ii, const int64_t *jj, int64_t
     p->off_ejj = take(sizeof(int) * std::max<int64_t>(E, 1));
     p->off_gbase = take(sizeof(long long) * (K + 1));
     p->off_mbase = take(sizeof(long long) * (K + 1));
+    p->off_pslot = take(sizeof(int) * n_frames);
+    p->off_prow = take(sizeof(int) * n_frames);
+    p->off_fprob = take(sizeof(int) * K);
+    p->off_phoff = take(sizeof(long long) * C);
+    p->off_pnpad = take(sizeof(int) * C);
+    p->off_pn = take(sizeof(int) * C);
+    p->off_prow0 = take(sizeof(int) * C);
     p->idx_bytes = off;
     p->off_epart = take(sizeof(float) * (size_t)std::max<int64_t>(E, 1) * p->ntile * kEdgeStride);
     p->off_gpart = take(sizeof(float) * (size_t)std::max<long long>(p->gbase[K], 1));
     p->off_msc = take(sizeof(double) * (size_t)std::max<long long>(p->mbase[K], 1));
     p->off_q = take(sizeof(float) * (size_t)K * p->HW);
     p->off_qw = take(sizeof(float) * (size_t)K * p->HW);
-    p->off_sys = take(sizeof(double) * ((size_t)p->npad * p->npad + 2 * (size_t)p->npad));  // [H ; b ; diag(A)]
-    p->off_dx = take(sizeof(double) * (size_t)p->npad);  // 1/diag(L) of the factorisation
+    p->off_sys = take(sizeof(double) * p->sys_doubles);  // per problem [H ; b ; diag(A)]
+    p->off_dx = take(sizeof(double) * (size_t)p->npad);  // 1/diag(L) of the factorisation (single-problem path)
     p->off_flag = take(sizeof(int) * chol_scratch_ints(p->npad));
     p->flag_bytes = sizeof(int) * chol_scratch_ints(p->npad);
     p->total = off;
@@ -265,9 +327,31 @@ extern "C" int vipe_ba_plan_create(const int64_t *ii, const int64_t *jj, int64_t
     }
     std::memcpy(p->blob.data() + p->off_gbase, p->gbase.data(), sizeof(long long) * (K + 1));
     std::memcpy(p->blob.data() + p->off_mbase, p->mbase.data(), sizeof(long long) * (K + 1));
+    std::memcpy(p->blob.data() + p->off_pslot, p->pose_slot.data(), sizeof(int) * n_frames);
+    std::memcpy(p->blob.data() + p->off_prow, p->pose_row.data(), sizeof(int) * n_frames);
+    std::memcpy(p->blob.data() + p->off_fprob, p->frame_prob.data(), sizeof(int) * K);
+    std::memcpy(p->blob.data() + p->off_phoff, p->prob_hoff.data(), sizeof(long long) * C);
+    std::memcpy(p->blob.data() + p->off_pnpad, p->prob_npad.data(), sizeof(int) * C);
+    std::memcpy(p->blob.data() + p->off_pn, p->prob_n.data(), sizeof(int) * C);
+    std::memcpy(p->blob.data() + p->off_prow0, p->prob_row0.data(), sizeof(int) * C);
     *out = p;
     return 0;
 }
+
+extern "C" int vipe_ba_plan_create(const int64_t *ii, const int64_t *jj, int64_t n_edges, int64_t n_frames, int ht,
+                                   int wd, int t0, int t1, int rank, int world, vipe_ba_plan **out) {
+    if (t0 < 0 || t1 < t0 || t1 > n_frames) return fail("need 0 <= t0 <= t1 <= n_frames");
+    const int64_t fp[2] = {0, n_frames}, a0[1] = {t0}, a1[1] = {t1};
+    return plan_create_impl(ii, jj, n_edges, n_frames, ht, wd, 1, fp, a0, a1, rank, world, out);
+}
+
+extern "C" int vipe_ba_plan_create_batch(const int64_t *ii, const int64_t *jj, int64_t n_edges, int64_t n_frames, int ht,
+                                         int wd, int n_problems, const int64_t *frame_ptr, const int64_t *t0s,
+                                         const int64_t *t1s, vipe_ba_plan **out) {
+    if (n_problems < 1 || !frame_ptr || !t0s || !t1s) return fail("bad batch description");
+    return plan_create_impl(ii, jj, n_edges, n_frames, ht, wd, n_problems, frame_ptr, t0s, t1s, 0, 1, out);
+}
+extern "C" int64_t vipe_ba_plan_num_free_poses(const vipe_ba_plan *p) { return p ? p->P : -1; }
 
 extern "C" void vipe_ba_plan_destroy(vipe_ba_plan *plan) { delete plan; }
 extern "C" int64_t vipe_ba_plan_num_kx(const vipe_ba_plan *p) { return p ? p->K : -1; }
@@ -319,9 +403,14 @@ static Tables make_tables(const vipe_ba_plan *p, void *ws) {
     tb.N = (int)p->N;
     tb.HW = p->HW;
     tb.wd = p->wd;
-    tb.t0 = p->t0;
-    tb.t1 = p->t1;
-    tb.P = p->P;
+    tb.pose_slot = (const int *)(w + p->off_pslot);
+    tb.pose_row = (const int *)(w + p->off_prow);
+    tb.frame_prob = (const int *)(w + p->off_fprob);
+    tb.prob_hoff = (const long long *)(w + p->off_phoff);
+    tb.prob_npad = (const int *)(w + p->off_pnpad);
+    tb.prob_n = (const int *)(w + p->off_pn);
+    tb.prob_row0 = (const int *)(w + p->off_prow0);
+    tb.C = p->C;
     tb.ntile = p->ntile;
     tb.k_lo = p->k_lo;
     tb.k_hi = p->k_hi;
@@ -352,8 +441,11 @@ static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void 
     unsigned char *w = (unsigned char *)ws;
     double *H = (double *)(w + p->off_sys);
     double *b = H + (size_t)p->npad * p->npad;
-    VBA_CUDA(launch_system_clear(H, b, p->n, p->npad, st));
-    p->launches += (p->npad > p->n) ? 2 : 1;
+    {
+        const Tables t0b = make_tables(p, ws);
+        VBA_CUDA(launch_system_clear(H, p->sys_doubles, t0b.prob_hoff, t0b.prob_n, t0b.prob_npad, p->C, p->any_padding, st));
+    }
+    p->launches += p->any_padding ? 2 : 1;
     const int nframes = p->k_hi - p->k_lo;
     if (nframes <= 0 || p->P <= 0) return 0;
 
@@ -385,9 +477,6 @@ static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void 
     ra.gpart = la.gpart;
     ra.msc = (double *)(w + p->off_msc);
     ra.hsys = H;
-    ra.bsys = b;
-    ra.adiag = b + p->npad;
-    ra.n = p->npad;
     ra.motion_only = motion_only;
     VBA_CUDA(launch_frame_reduce(ra, nframes, std::max(p->dmax, 1), st));
     p->launches++;
@@ -410,8 +499,14 @@ static int solve_update_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, vo
     int *scratch = (int *)(w + p->off_flag);
     int cnt = 0;
     p->epoch++;
-    VBA_CUDA(launch_damped_solve(H, b, p->n, p->npad, lm, ep, t->dx_out, scratch, (double *)(w + p->off_dx),
-                                 p->opt.damp_on_pose_hessian ? b + p->npad : nullptr, p->epoch, st, &cnt));
+    const Tables tbs = make_tables(p, ws);
+    if (p->C == 1) {
+        VBA_CUDA(launch_damped_solve(H, b, p->n, p->npad, lm, ep, t->dx_out, scratch, (double *)(w + p->off_dx),
+                                     p->opt.damp_on_pose_hessian ? b + p->npad : nullptr, p->epoch, st, &cnt));
+    } else {  // many small independent problems: one CTA each
+        VBA_CUDA(launch_small_solve_batch(H, tbs.prob_hoff, tbs.prob_n, tbs.prob_npad, tbs.prob_row0, p->C, lm, ep, t->dx_out,
+                                          p->opt.damp_on_pose_hessian != 0, st, &cnt));
+    }
     p->launches += cnt;
     if (mid) VBA_CUDA(cudaEventRecord(mid, st));
     const int nframes = p->k_hi - p->k_lo;
@@ -430,7 +525,7 @@ static int solve_update_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, vo
         VBA_CUDA(launch_backsub(ba, nframes, std::max(p->dmax, 1), st));
         p->launches++;
     }
-    VBA_CUDA(launch_pose_retr(t->poses, t->dx_out, p->t0, p->t1, p->opt.renorm_quat, st));
+    VBA_CUDA(launch_pose_retr(t->poses, t->dx_out, tbs.pose_row, (int)p->N, p->opt.renorm_quat, st));
     p->launches++;
     return 0;
 }

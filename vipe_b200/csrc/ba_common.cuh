@@ -23,7 +23,15 @@ struct Tables {
     const int *e_jj;    // [E]   edge id -> target frame
     const long long *gbase;  // [K+1] float offset of frame k's Gram partials (already multiplied by ntile)
     const long long *mbase;  // [K+1] double offset of frame k's M scratch
-    int K, E, N, HW, wd, t0, t1, P, ntile, k_lo, k_hi;
+    // A plan holds C >= 1 independent problems (C > 1: batched small problems, e.g. many motion-only clips).
+    const int *pose_slot;        // [N] index of the pose in ITS problem's reduced system, -1 if fixed
+    const int *pose_row;         // [N] row of the pose in the concatenated dx output, -1 if fixed
+    const int *frame_prob;       // [K] problem of kx frame k
+    const long long *prob_hoff;  // [C] double offset of the problem's [H ; b ; diag(A)] block
+    const int *prob_npad;        // [C] padded system size of the problem
+    const int *prob_n;           // [C] system size 6 * (free poses)
+    const int *prob_row0;        // [C] first dx row of the problem
+    int K, E, N, HW, wd, ntile, k_lo, k_hi, C;
 };
 
 // Semantic switches (defaults = the reference's CUDA BA; the other values serve the conventions of vipe/slam's Python BA,
@@ -75,10 +83,8 @@ struct ReduceArgs {
     const float *poses;
     const float *epart, *gpart;
     double *msc;   // M scratch
-    double *hsys;  // [n*n] row-major, lower triangle (+ full diagonal blocks)
-    double *bsys;  // [n]
-    double *adiag; // [n] diagonal of the pose Hessian A alone (before the Schur complement), for damp_on_pose_hessian
-    int n;
+    double *hsys;  // per problem: [n*n] row-major lower triangle (+ full diagonal blocks), then b [n], then diag(A) [n]
+                   //   (diag(A): the pose Hessian alone, before the Schur complement, for damp_on_pose_hessian)
     int motion_only;
 };
 

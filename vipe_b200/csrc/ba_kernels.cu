@@ -342,9 +342,13 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
     const int s0 = tb.fptr[k];
     const int d = tb.fptr[k + 1] - s0;
     if (d == 0) return;
-    const int P = tb.P, n = a.n, ntile = tb.ntile;
-    const int ai_raw = src - tb.t0;
-    const int ai = (ai_raw >= 0 && ai_raw < P) ? ai_raw : -1;
+    const int ntile = tb.ntile;
+    const int prob = tb.frame_prob[k];
+    const int n = tb.prob_npad[prob];
+    double *const hsys = a.hsys + tb.prob_hoff[prob];
+    double *const bsys = hsys + (size_t)n * n;
+    double *const adiag = bsys + n;
+    const int ai = tb.pose_slot[src];
 
     double *G = dsm;            // [d][36]
     double *T = G + d * 36;     // [d][36]
@@ -358,8 +362,7 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
         RelPose<double> rp;
         relative_pose<double>(a.poses, src, j, rp);
         adjoint_G<double>(rp, G + m * 36);
-        const int ajr = j - tb.t0;
-        aj[m] = (!rp.stereo && ajr >= 0 && ajr < P) ? ajr : -1;
+        aj[m] = rp.stereo ? -1 : tb.pose_slot[j];
     }
     for (int idx = tid; idx < d * kEdgeVals; idx += NT) {
         const int m = idx / kEdgeVals, r = idx - m * kEdgeVals;
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
             for (int t = 0; t < ntile; t++) s += (double)gp[(size_t)t * rec + npairs * 36 + idx];
         const double g = hs[m * kEdgeVals + 20 + r] - s;
         gv[idx] = g;
-        if (aj[m] >= 0) atomicAdd(a.bsys + 6 * aj[m] + r, g);
+        if (aj[m] >= 0) atomicAdd(bsys + 6 * aj[m] + r, g);
     }
     // M blocks
     for (int idx = tid; idx < npairs * 36; idx += NT) {
@@ -399,18 +402,18 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
             const int hi = r >= c ? r : c, lo = r >= c ? c : r;
             const int sl = hslot(hi, lo);
             if (sl >= 0) v += hs[m * kEdgeVals + sl];
-            if (r == c && sl >= 0 && aj[m] >= 0) atomicAdd(a.adiag + 6 * aj[m] + r, hs[m * kEdgeVals + sl]);
+            if (r == c && sl >= 0 && aj[m] >= 0) atomicAdd(adiag + 6 * aj[m] + r, hs[m * kEdgeVals + sl]);
         }
         msc[idx] = v;
         const int pa = aj[m], pb = aj[mp];
         if (pa >= 0 && pb >= 0) {
             if (m == mp) {
-                atomicAdd(a.hsys + (size_t)(6 * pa + r) * n + 6 * pa + c, v);
+                atomicAdd(hsys + (size_t)(6 * pa + r) * n + 6 * pa + c, v);
             } else if (pa == pb) {  // two edges into the same target pose: M + M^T on the diagonal block
-                atomicAdd(a.hsys + (size_t)(6 * pa + r) * n + 6 * pa + c, v);
-                atomicAdd(a.hsys + (size_t)(6 * pa + c) * n + 6 * pa + r, v);
+                atomicAdd(hsys + (size_t)(6 * pa + r) * n + 6 * pa + c, v);
+                atomicAdd(hsys + (size_t)(6 * pa + c) * n + 6 * pa + r, v);
             } else {
-                add_block_entry(a.hsys, n, pa, r, pb, c, v);
+                add_block_entry(hsys, n, pa, r, pb, c, v);
             }
         }
     }
@@ -435,7 +438,7 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
             }
         }
         T[idx] = s;
-        if (aj[mp] >= 0) add_block_entry(a.hsys, n, ai, r, aj[mp], c, s);
+        if (aj[mp] >= 0) add_block_entry(hsys, n, ai, r, aj[mp], c, s);
     }
     __syncthreads();
     // Z = sum_m' T_m' G_m'^T  -> block (i,i);   rhs(i) += sum_m G_m g_m
@@ -446,7 +449,7 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
 #pragma unroll
             for (int q = 0; q < 6; q++) s += T[mp * 36 + r * 6 + q] * G[mp * 36 + c * 6 + q];
         }
-        atomicAdd(a.hsys + (size_t)(6 * ai + r) * n + 6 * ai + c, s);
+        atomicAdd(hsys + (size_t)(6 * ai + r) * n + 6 * ai + c, s);
     } else if (tid >= 64 && tid < 70) {
         const int r = tid - 64;
         double s = 0.0;
@@ -454,7 +457,7 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
 #pragma unroll
             for (int q = 0; q < 6; q++) s += G[m * 36 + r * 6 + q] * gv[m * 6 + q];
         }
-        atomicAdd(a.bsys + 6 * ai + r, s);
+        atomicAdd(bsys + 6 * ai + r, s);
     } else if (tid >= 96 && tid < 102) {
         // diagonal of sum_m G_m H_jj,m G_m^T alone (the source pose's Hessian before the Schur complement)
         const int r = tid - 96;
@@ -467,7 +470,7 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
                     if (sl >= 0) s += Gm[p] * hs[m * kEdgeVals + sl] * Gm[q];
                 }
         }
-        atomicAdd(a.adiag + 6 * ai + r, s);
+        atomicAdd(adiag + 6 * ai + r, s);
     }
 }
 
@@ -486,7 +489,7 @@ __global__ void __launch_bounds__(NT) backsub_kernel(const BackArgs a) {
     const int src = tb.kx[k];
     const int s0 = tb.fptr[k];
     const int d = tb.fptr[k + 1] - s0;
-    const int HW = tb.HW, P = tb.P;
+    const int HW = tb.HW;
     float *ec = smem;                   // [d][16]
     float *ys = ec + d * kEcStride;     // [d][8]
 
@@ -498,16 +501,16 @@ __global__ void __launch_bounds__(NT) backsub_kernel(const BackArgs a) {
         write_edge_consts(ec + m * kEcStride, rp, e);
         float G[36];
         adjoint_G<float>(rp, G);
-        const int ai = src - tb.t0, aj = j - tb.t0;
-        const int lo = a.opt.backsub_all_poses ? 0 : 1;  // Q4: the reference skips pose index 0 on purpose
-        const bool vi = ai >= lo && ai < P, vj = aj >= lo && aj < P;
+        const int lo = a.opt.backsub_all_poses ? 0 : 1;  // Q4: the reference skips pose index 0 (of its problem) on purpose
+        const bool vi = tb.pose_slot[src] >= lo, vj = tb.pose_slot[j] >= lo;
+        const int ri = tb.pose_row[src], rj = tb.pose_row[j];
         float y[6];
 #pragma unroll
         for (int c = 0; c < 6; c++) {
-            float s = vj ? a.dx[6 * aj + c] : 0.0f;
+            float s = vj ? a.dx[6 * rj + c] : 0.0f;
             if (vi) {
 #pragma unroll
-                for (int r = 0; r < 6; r++) s = fmaf(G[6 * r + c], a.dx[6 * ai + r], s);
+                for (int r = 0; r < 6; r++) s = fmaf(G[6 * r + c], a.dx[6 * ri + r], s);
             }
             y[c] = s;
         }
@@ -568,12 +571,15 @@ __global__ void __launch_bounds__(NT) backsub_kernel(const BackArgs a) {
 // =================================================================================================
 // Stage 4b: pose retraction T <- exp(xi) T without quaternion renormalisation
 // (pose_retr_kernel / retrSE3 / expSE3 / expSO3, geom_kernels.cu:116-177,882-931).
-__global__ void pose_retr_kernel(float *__restrict__ poses, const float *__restrict__ dx, int t0, int t1, int renorm) {
-    const int kk = t0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (kk >= t1) return;
+__global__ void pose_retr_kernel(float *__restrict__ poses, const float *__restrict__ dx, const int *__restrict__ pose_row,
+                                 int n_poses, int renorm) {
+    const int kk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kk >= n_poses) return;
+    const int row = pose_row[kk];
+    if (row < 0) return;
     float xi[6];
 #pragma unroll
-    for (int n = 0; n < 6; n++) xi[n] = dx[6 * (kk - t0) + n];
+    for (int n = 0; n < 6; n++) xi[n] = dx[6 * row + n];
     const float t[3] = {poses[7 * kk], poses[7 * kk + 1], poses[7 * kk + 2]};
     const float q[4] = {poses[7 * kk + 3], poses[7 * kk + 4], poses[7 * kk + 5], poses[7 * kk + 6]};
     // expSO3
@@ -703,10 +709,9 @@ cudaError_t launch_backsub(const BackArgs &a, int nframes, int dmax, cudaStream_
     return launch_back_t<128, 1>(a, nframes, dmax, st);
 }
 
-cudaError_t launch_pose_retr(float *poses, const float *dx, int t0, int t1, int renorm, cudaStream_t st) {
-    const int P = t1 - t0;
-    if (P <= 0) return cudaSuccess;
-    pose_retr_kernel<<<(P + 127) / 128, 128, 0, st>>>(poses, dx, t0, t1, renorm);
+cudaError_t launch_pose_retr(float *poses, const float *dx, const int *pose_row, int n_poses, int renorm, cudaStream_t st) {
+    if (n_poses <= 0) return cudaSuccess;
+    pose_retr_kernel<<<(n_poses + 127) / 128, 128, 0, st>>>(poses, dx, pose_row, n_poses, renorm);
     return cudaGetLastError();
 }
 

@@ -16,7 +16,7 @@ bool tile_config2(int HW, int dmax, bool motion, int &NT);
 cudaError_t launch_linearize2(const LinArgs &a, int nframes, int dmax, bool motion, int NT, cudaStream_t st);
 cudaError_t launch_frame_reduce(const ReduceArgs &a, int nframes, int dmax, cudaStream_t st);
 cudaError_t launch_backsub(const BackArgs &a, int nframes, int dmax, cudaStream_t st);
-cudaError_t launch_pose_retr(float *poses, const float *dx, int t0, int t1, int renorm, cudaStream_t st);
+cudaError_t launch_pose_retr(float *poses, const float *dx, const int *pose_row, int n_poses, int renorm, cudaStream_t st);
 
 // Dense damped Cholesky solve of the reduced camera system (chol.cu).
 //   H: [npad x npad] fp64 row-major, lower triangle valid on entry (destroyed);  b: [npad] fp64 (destroyed)
@@ -28,8 +28,13 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
                                 double *dinv /*[npad]*/, const double *dampdiag /*[npad] or null*/, int epoch, cudaStream_t st,
                                 int *launches);
 size_t chol_scratch_ints(int npad);
-// zero [H ; b] and put the identity on the padded diagonal
-cudaError_t launch_system_clear(double *H, double *b, int n, int npad, cudaStream_t st);
+// zero every problem's [H ; b ; diag(A)] block and put the identity on the padded diagonals
+cudaError_t launch_system_clear(double *sys, size_t total_doubles, const long long *prob_hoff, const int *prob_n,
+                                const int *prob_npad, int n_prob, bool any_padding, cudaStream_t st);
+// batched solve of C > 1 small problems (each at most 2 tiles), one CTA per problem
+cudaError_t launch_small_solve_batch(double *sys, const long long *prob_hoff, const int *prob_n, const int *prob_npad,
+                                     const int *prob_row0, int n_prob, float lm, float ep, float *dx, bool damp_on_A,
+                                     cudaStream_t st, int *launches);
 
 constexpr int kCholBlock = 64;
 

@@ -20,18 +20,19 @@ constexpr int CT = 256;         // threads per CTA
 constexpr int DL = TB + 1;      // row stride of row-major tiles in shared memory (conflict-free column access)
 
 // ------------------------------------------------------------------------------------------------
-__global__ void pad_identity_kernel(double *H, int n, int npad) {
-    const int i = n + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < npad) H[(size_t)i * npad + i] = 1.0;
+__global__ void pad_identity_kernel(double *sys, const long long *prob_hoff, const int *prob_n, const int *prob_npad) {
+    const int c = blockIdx.x;
+    double *H = sys + prob_hoff[c];
+    const int n = prob_n[c], npad = prob_npad[c];
+    for (int i = n + threadIdx.x; i < npad; i += blockDim.x) H[(size_t)i * npad + i] = 1.0;
 }
 
-cudaError_t launch_system_clear(double *H, double *b, int n, int npad, cudaStream_t st) {
-    // H, b and the pose-Hessian diagonal are contiguous ([npad*npad], [npad], [npad])
-    cudaError_t err = cudaMemsetAsync(H, 0, ((size_t)npad * npad + 2 * (size_t)npad) * sizeof(double), st);
+cudaError_t launch_system_clear(double *sys, size_t total_doubles, const long long *prob_hoff, const int *prob_n,
+                                const int *prob_npad, int n_prob, bool any_padding, cudaStream_t st) {
+    cudaError_t err = cudaMemsetAsync(sys, 0, total_doubles * sizeof(double), st);
     if (err != cudaSuccess) return err;
-    (void)b;
-    if (npad > n) {
-        pad_identity_kernel<<<1, 64, 0, st>>>(H, n, npad);
+    if (any_padding) {
+        pad_identity_kernel<<<n_prob, 64, 0, st>>>(sys, prob_hoff, prob_n, prob_npad);
         return cudaGetLastError();
     }
     return cudaSuccess;
@@ -720,10 +721,25 @@ __device__ void smem_trsv_bwd(const double *L, const double *dinv, double *v, in
     v[lane + 32] = v1;
 }
 
+// Batched form: blockIdx.x selects the problem when `prob_hoff` is non-null (many small independent problems, e.g.
+// 64 motion-only clips); otherwise the explicit H / b / n / ld arguments describe the one problem.
 __global__ void __launch_bounds__(CT) chol_small_kernel(const double *__restrict__ H, const double *__restrict__ b, int n,
                                                         int ld, int T, float lm, float ep, float *__restrict__ dx,
-                                                        const double *__restrict__ dampdiag) {
+                                                        const double *__restrict__ dampdiag,
+                                                        const long long *__restrict__ prob_hoff, const int *__restrict__ prob_n,
+                                                        const int *__restrict__ prob_npad, const int *__restrict__ prob_row0,
+                                                        int damp_on_A) {
     extern __shared__ __align__(16) double sm[];
+    if (prob_hoff) {
+        const int c = blockIdx.x;
+        ld = prob_npad[c];
+        n = prob_n[c];
+        T = ld / TB;
+        H = H + prob_hoff[c];
+        b = H + (size_t)ld * ld;
+        dampdiag = damp_on_A ? b + ld : nullptr;
+        dx = dx + 6 * (size_t)prob_row0[c];
+    }
     double *A00 = sm;                   // [64][DL]
     double *A10 = A00 + TB * DL;        // [64][DL]
     double *A11 = A10 + TB * DL;        // [64][DL]
@@ -823,7 +839,19 @@ static cudaError_t launch_small_solve(double *H, double *b, int n, int npad, flo
     const size_t sm = (size_t)(3 * TB * DL + TB * LD + 3 * TB + 32 * 34 + 2 * TB) * sizeof(double);
     cudaError_t err = cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (err != cudaSuccess) return err;
-    chol_small_kernel<<<1, CT, sm, st>>>(H, b, n, npad, npad / TB, lm, ep, dx, dampdiag);
+    chol_small_kernel<<<1, CT, sm, st>>>(H, b, n, npad, npad / TB, lm, ep, dx, dampdiag, nullptr, nullptr, nullptr, nullptr, 0);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_small_solve_batch(double *sys, const long long *prob_hoff, const int *prob_n, const int *prob_npad,
+                                     const int *prob_row0, int n_prob, float lm, float ep, float *dx, bool damp_on_A,
+                                     cudaStream_t st, int *launches) {
+    const size_t sm = (size_t)(3 * TB * DL + TB * LD + 3 * TB + 32 * 34 + 2 * TB) * sizeof(double);
+    cudaError_t err = cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (err != cudaSuccess) return err;
+    chol_small_kernel<<<n_prob, CT, sm, st>>>(sys, nullptr, 0, 0, 0, lm, ep, dx, nullptr, prob_hoff, prob_n, prob_npad,
+                                             prob_row0, damp_on_A ? 1 : 0);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -16,7 +16,7 @@ import torch
 from .. import _lib
 from ..plan import BAPlan, cached_plan
 
-__all__ = ["ba", "ba_plan", "projmap", "frame_distance", "depth_filter", "iproj"]
+__all__ = ["ba", "ba_batch", "ba_plan", "projmap", "frame_distance", "depth_filter", "iproj"]
 
 
 def _check_contiguous(**tensors):
@@ -111,6 +111,46 @@ def ba(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, 
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(_lib.lib().vipe_ba_run(plan.handle, C.byref(tens), ws.data_ptr(), iterations, float(lm), float(ep),
                                           int(motion_only), stream), "vipe_ba_run")
+    return [dx, dz if dz is not None else torch.empty(0, device=dev)]
+
+
+_BATCH_PLANS: dict = {}
+
+
+def ba_batch(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, frame_ptr, t0s, t1s, iterations, lm, ep,
+             motion_only):
+    """Many independent small BA problems in one set of launches (BASELINE config 5: motion-only BA of 64 clips).
+
+    Not a reference entry point: the reference would call `slam_ext.ba` once per clip.  Tensors are the
+    concatenation of the per-clip arguments of `ba` (poses[sum N,7], disps[sum N,ht,wd], targets[sum E,2,ht,wd], ...;
+    `ii/jj` hold GLOBAL frame ids); problem c owns frames `[frame_ptr[c], frame_ptr[c+1])` and optimises its window
+    `[t0s[c], t1s[c])`.  Every problem behaves exactly like its own `ba` call.  Returns `[dx[sum P,6], dz[K,ht*wd]]`."""
+    dev, N, ht, wd, E = validate(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, 0, 0, motion_only)
+    motion_only = bool(motion_only)
+    fp = torch.as_tensor(frame_ptr, dtype=torch.int64).cpu()
+    t0s_h = torch.as_tensor(t0s, dtype=torch.int64).cpu()
+    t1s_h = torch.as_tensor(t1s, dtype=torch.int64).cpu()
+    ii_h, jj_h = ii.detach().to("cpu", torch.int64).contiguous(), jj.detach().to("cpu", torch.int64).contiguous()
+    key = (ii_h.numpy().tobytes(), jj_h.numpy().tobytes(), fp.numpy().tobytes(), t0s_h.numpy().tobytes(), t1s_h.numpy().tobytes(), N, ht, wd)
+    plan = _BATCH_PLANS.get(key)
+    if plan is None:
+        if len(_BATCH_PLANS) >= 4:
+            _BATCH_PLANS.pop(next(iter(_BATCH_PLANS)))
+        plan = _BATCH_PLANS[key] = BAPlan(ii_h, jj_h, N, ht, wd, 0, 0, batch=(fp, t0s_h, t1s_h))
+    K, HW, P = plan.K, ht * wd, plan.P
+    dx = torch.zeros(P, 6, dtype=torch.float32, device=dev)
+    dz = None
+    if not motion_only:
+        if eta.numel() != K * HW:
+            raise RuntimeError(f"eta must be viewable as [K={K}, ht*wd]")
+        eta = eta.contiguous()
+        dz = torch.zeros(K, HW, dtype=torch.float32, device=dev)
+    if int(iterations) > 0 and P > 0:
+        with torch.cuda.device(dev):
+            ws = plan.workspace(dev)
+            tens = _tensors(poses, disps, intrinsics, disps_sens, targets, weights, eta, dx, dz, motion_only)
+            _lib.check(_lib.lib().vipe_ba_run(plan.handle, C.byref(tens), ws.data_ptr(), int(iterations), float(lm), float(ep),
+                                              int(motion_only), torch.cuda.current_stream(dev).cuda_stream), "vipe_ba_run")
     return [dx, dz if dz is not None else torch.empty(0, device=dev)]
 
 

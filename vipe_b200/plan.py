@@ -18,7 +18,9 @@ class BAPlan:
     torch caching allocator and uploads the index tables into its head."""
 
     def __init__(self, ii: torch.Tensor, jj: torch.Tensor, n_frames: int, ht: int, wd: int, t0: int, t1: int,
-                 rank: int = 0, world: int = 1):
+                 rank: int = 0, world: int = 1, batch=None):
+        """`batch = (frame_ptr, t0s, t1s)` (int64 host tensors) builds a batched plan of independent small problems
+        (vipe_ba_plan_create_batch); t0/t1 are then ignored."""
         L = _lib.lib()
         ii_h = ii.detach().to("cpu", torch.int64).contiguous()
         jj_h = jj.detach().to("cpu", torch.int64).contiguous()
@@ -29,10 +31,17 @@ class BAPlan:
         self.P = self.t1 - self.t0
         self.rank, self.world = rank, world
         h = C.c_void_p()
-        _lib.check(L.vipe_ba_plan_create(ii_h.data_ptr(), jj_h.data_ptr(), self.E, self.N, self.ht, self.wd, self.t0,
-                                         self.t1, rank, world, C.byref(h)), "vipe_ba_plan_create")
+        if batch is None:
+            _lib.check(L.vipe_ba_plan_create(ii_h.data_ptr(), jj_h.data_ptr(), self.E, self.N, self.ht, self.wd, self.t0,
+                                             self.t1, rank, world, C.byref(h)), "vipe_ba_plan_create")
+        else:
+            fp, t0s, t1s = [torch.as_tensor(x, dtype=torch.int64).contiguous() for x in batch]
+            _lib.check(L.vipe_ba_plan_create_batch(ii_h.data_ptr(), jj_h.data_ptr(), self.E, self.N, self.ht, self.wd,
+                                                   int(t0s.numel()), fp.data_ptr(), t0s.data_ptr(), t1s.data_ptr(), C.byref(h)),
+                       "vipe_ba_plan_create_batch")
         self._h = h
         self.K = int(L.vipe_ba_plan_num_kx(h))
+        self.P = int(L.vipe_ba_plan_num_free_poses(h))
         self._ws: dict = {}
 
     def __del__(self):

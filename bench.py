@@ -337,14 +337,15 @@ def main():
     iters_total = args.steps * cfg.iters * clips
     value = iters_total / (total_ms / 1e3)
     edge_px = E * HW
-    it_bytes, lin_bytes = algorithmic_bytes(cfg, E, K, N, HW, cfg.motion_only)
+    nprob = len(problems) if batched else 1  # a batched step processes this rank's clips in one launch set
+    it_bytes, lin_bytes = algorithmic_bytes(cfg, E * nprob, K * nprob, N * nprob, HW, cfg.motion_only)
     peak, peak_src = measured_peaks()
 
     # fp32 work of the fused kernel (it is FMA-bound, not HBM-bound, at backend degrees): ~110 FMA-pipe lane-ops per
     # edge-pixel for the linearisation + 36 per block pair and frame-pixel for the Schur Gram
     deg = torch.bincount(pr.ii, minlength=N).double()
     gram_ops = float((36.0 * deg * (deg + 1) / 2 + 12.0 * deg).sum()) * HW
-    lin_fma_ops = 110.0 * E * HW + (0.0 if cfg.motion_only else gram_ops)
+    lin_fma_ops = (110.0 * E * HW + (0.0 if cfg.motion_only else gram_ops)) * nprob
     FP32_PEAK_TFMA = 34.3  # measured on this pool: FFMA/FFMA2 full-chip micro-benchmark (scripts/ffma2_micro.cu), TFMA/s
     roofline = None
     if sharded:
@@ -374,7 +375,7 @@ def main():
                                 "frac": lin_fma_ops / (lin_ms * 1e-3) / 1e12 / FP32_PEAK_TFMA,
                                 "note": "the fused Jacobian+Schur kernel is FMA-bound at backend degrees; see DESIGN.md section 4"},
                     "whole_iteration": {"algorithmic_bytes": it_bytes,
-                                        "achieved_gbs": it_bytes * cfg.iters * clips * args.steps / (total_ms * 1e-3) / 1e9 / max(world, 1)}}
+                                        "achieved_gbs": it_bytes * cfg.iters * (clips // nprob if batched else clips) * args.steps / (total_ms * 1e-3) / 1e9 / max(world, 1)}}
         prof = ROOT / "profiles" / "traffic.json"
         if prof.is_file():
             try:

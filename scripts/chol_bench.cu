@@ -10,6 +10,38 @@
 using namespace vba;
 
 
+// timing-only variants of warp_potrf32 (results are wrong on purpose): where do the ~230 clk per pivot go?
+template <int VARIANT>
+__device__ __forceinline__ void potrf32_variant(double (&a)[32], double *colbuf, int lane) {
+    double diag = 0.0;
+#pragma unroll
+    for (int c = 0; c < 32; c++)
+        if (lane == c) diag = a[c];
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const double piv = (VARIANT == 3) ? diag : __shfl_sync(0xffffffffu, diag, j);  // 3: no shuffle
+        double inv;
+        if (VARIANT == 1) { asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(piv)); }   // 1: seed only
+        else if (VARIANT == 2) inv = piv * 0.001;                                           // 2: no rsqrt at all
+        else inv = fast_rsqrt(piv);
+        double l = ((lane == j) ? piv : a[j]) * inv;
+        if (lane < j) l = 0.0;
+        a[j] = l;
+        diag = fma(-l, l, diag);
+        if (VARIANT == 4) {  // 4: no column exchange (use own value)
+#pragma unroll
+            for (int k = j + 1; k < 32; k++) a[k] = fma(-l, l, a[k]);
+        } else {
+            double *cb = colbuf + (j & 1) * 32;
+            cb[lane] = l;
+            __syncwarp();
+#pragma unroll
+            for (int k = j + 1; k < 32; k++) a[k] = fma(-l, cb[k], a[k]);
+        }
+    }
+    __syncwarp();
+}
+
 // ---- micro timing of the tile primitives (single CTA), cycles via clock64
 __global__ void __launch_bounds__(CT) micro_kernel(double *out, long long *clk) {
     extern __shared__ __align__(16) double sm[];
@@ -44,6 +76,16 @@ __global__ void __launch_bounds__(CT) micro_kernel(double *out, long long *clk) 
         }
         t2 = tt[3];
         t3 = tt[4];
+#define TIME_VARIANT(V)                                                                        \
+        for (int rep = 0; rep < 3; rep++) {                                                    \
+            for (int c = 0; c < 32; c++) a[c] = (lane == c) ? 100.0 + c + rep : 1.0 / (1 + abs(lane - c)); \
+            long long q0 = clock64();                                                          \
+            potrf32_variant<V>(a, col, lane);                                                  \
+            long long q1 = clock64();                                                          \
+            if (lane == 0 && rep == 2) clk[16 + V] = q1 - q0;                                  \
+            out[lane] += a[lane & 31];                                                         \
+        }
+        TIME_VARIANT(0) TIME_VARIANT(1) TIME_VARIANT(2) TIME_VARIANT(3) TIME_VARIANT(4)
         warp_trsm32<34>(a, Ltd, dinv);
         t4 = clock64();
         out[lane] = a[lane & 31] + inv;
@@ -79,6 +121,8 @@ int main(int argc, char **argv) {
             cudaMemcpy(h, clk, 40, cudaMemcpyDeviceToHost);
             cudaMemcpy(h2, clk + 8, 32, cudaMemcpyDeviceToHost);
             printf("warp_potrf32 repeated in a loop: %lld %lld %lld %lld\n", h2[0], h2[1], h2[2], h2[3]);
+            long long h3[5]; cudaMemcpy(h3, clk + 16, 40, cudaMemcpyDeviceToHost);
+            printf("variants (warm): full %lld | rsqrt seed only %lld | no rsqrt %lld | no pivot shuffle %lld | no column exchange %lld\n", h3[0], h3[1], h3[2], h3[3], h3[4]);
             printf("cycles: tile_potrf64 %lld | warp_potrf32 %lld | warp_trsm32 %lld | tile_trsm64 %lld | tile_gemm_sub %lld   (%s)\n", h[0], h[1], h[2], h[3], h[4], cudaGetErrorString(cudaGetLastError()));
         }
         return 0;

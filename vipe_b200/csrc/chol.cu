@@ -192,9 +192,10 @@ __device__ __forceinline__ bool warp_potrf32(double (&a)[32], double *colbuf, in
 #pragma unroll
     for (int j = 0; j < 32; j++) {
         const double piv = __shfl_sync(0xffffffffu, diag, j);
-        const bool good = (piv > 1e-290) && (piv < 1e290);  // also false for NaN
-        ok = ok && good;
-        const double inv = good ? fast_rsqrt(piv) : 0.0;
+        // the validity test stays OFF the dependency chain: a bad pivot poisons the tile with NaN/Inf, the flag makes
+        // the solve return dx = 0 anyway (geom_kernels.cu:1186-1188)
+        ok = ok && (piv > 1e-290) && (piv < 1e290);
+        const double inv = fast_rsqrt(piv);
         if (lane == j) my_inv = inv;
         double l = ((lane == j) ? piv : a[j]) * inv;  // lane j: piv * inv = sqrt(piv)
         if (lane < j) l = 0.0;

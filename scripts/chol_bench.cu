@@ -151,7 +151,7 @@ int main(int argc, char **argv) {
     const size_t sysn = (size_t)npad * npad + npad;
     cudaMalloc(&dsys, sysn * 8);
     cudaMalloc(&dH, sysn * 8);
-    cudaMalloc(&ddinv, npad * 8);
+    cudaMalloc(&ddinv, ((size_t)npad + (size_t)npad * 64) * 8);
     cudaMalloc(&ddx, npad * 4);
     const size_t nscr = chol_scratch_ints(npad);
     cudaMalloc(&dscr, nscr * 4);
@@ -172,7 +172,7 @@ int main(int argc, char **argv) {
         cudaDeviceSynchronize();
         int cnt = 0;
         cudaEventRecord(e0);
-        cudaError_t err = launch_damped_solve(dH, dH + (size_t)npad * npad, n, npad, 0.0f, 0.0f, ddx, dscr, ddinv, nullptr, r + 1, 0, &cnt);
+        cudaError_t err = launch_damped_solve(dH, dH + (size_t)npad * npad, n, npad, 0.0f, 0.0f, ddx, dscr, ddinv, ddinv + npad, nullptr, r + 1, 0, &cnt);
         cudaEventRecord(e1);
         cudaDeviceSynchronize();
         if (err != cudaSuccess || cudaGetLastError() != cudaSuccess) { printf("cuda error %s\n", cudaGetErrorString(err)); return 1; }

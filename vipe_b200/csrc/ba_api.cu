@@ -313,7 +313,7 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     p->off_q = take(sizeof(float) * (size_t)K * p->HW);
     p->off_qw = take(sizeof(float) * (size_t)K * p->HW);
     p->off_sys = take(sizeof(double) * p->sys_doubles);  // per problem [H ; b ; diag(A)]
-    p->off_dx = take(sizeof(double) * (size_t)p->npad);  // 1/diag(L) of the factorisation (single-problem path)
+    p->off_dx = take(sizeof(double) * ((size_t)p->npad + (size_t)p->npad * kCholBlock));  // 1/diag(L), then L_jj^-T tiles
     p->off_flag = take(sizeof(int) * chol_scratch_ints(p->npad));
     p->flag_bytes = sizeof(int) * chol_scratch_ints(p->npad);
     p->total = off;
@@ -502,7 +502,7 @@ static int solve_update_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, vo
     const Tables tbs = make_tables(p, ws);
     if (p->C == 1) {
         VBA_CUDA(launch_damped_solve(H, b, p->n, p->npad, lm, ep, t->dx_out, scratch, (double *)(w + p->off_dx),
-                                     p->opt.damp_on_pose_hessian ? b + p->npad : nullptr, p->epoch, st, &cnt));
+                                     (double *)(w + p->off_dx) + p->npad, p->opt.damp_on_pose_hessian ? b + p->npad : nullptr, p->epoch, st, &cnt));
     } else {  // many small independent problems: one CTA each
         VBA_CUDA(launch_small_solve_batch(H, tbs.prob_hoff, tbs.prob_n, tbs.prob_npad, tbs.prob_row0, p->C, lm, ep, t->dx_out,
                                           p->opt.damp_on_pose_hessian != 0, st, &cnt));

@@ -25,8 +25,8 @@ cudaError_t launch_pose_retr(float *poses, const float *dx, const int *pose_row,
 // `scratch` is chol_scratch_ints(npad) ints of device memory, zeroed once when the workspace is set up; `epoch` must be
 // a value never used before on this scratch (tile ready flags are epoch-valued so they need no per-solve reset).
 cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx, int *scratch,
-                                double *dinv /*[npad]*/, const double *dampdiag /*[npad] or null*/, int epoch, cudaStream_t st,
-                                int *launches);
+                                double *dinv /*[npad]*/, double *linvT /*[npad/64][4096]*/,
+                                const double *dampdiag /*[npad] or null*/, int epoch, cudaStream_t st, int *launches);
 size_t chol_scratch_ints(int npad);
 // zero every problem's [H ; b ; diag(A)] block and put the identity on the padded diagonals
 cudaError_t launch_system_clear(double *sys, size_t total_doubles, const long long *prob_hoff, const int *prob_n,

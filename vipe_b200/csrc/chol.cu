@@ -94,6 +94,7 @@ struct CholArgs {
     float *dx;
     double *dinv;  // [npad] 1 / diag(L)
     const double *dampdiag;  // [npad] or null: lm scales this instead of the matrix's own diagonal
+    double *linvT;           // [T][64*64] inverse-transposes of the diagonal tiles (for the backward substitution)
 };
 
 // Tile GEMM on the fp64 tensor cores (mma.sync.m8n8k4.f64 -> DMMA).  Measured on B200: DMMA issues at the full
@@ -585,6 +586,23 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
                 a.H[(size_t)(i0 + r) * ld + j0 + c] = (c <= r) ? As[r * RS + c] : 0.0;
             }
             if (tid < TB) a.dinv[j0 + tid] = dinv[tid];
+            TRACE(t, 5);
+            publish_flag(a.flags + (size_t)i * T + j, a.epoch);
+            TRACE(t, 6);
+            // Off the critical path (the tile is already published): L_jj^-T = I * L_jj^-T on the tensor cores, so that
+            // the backward substitution's per-block triangular solve becomes a 64x64 matrix-vector product.
+            for (int idx = tid; idx < TB * TB; idx += CT) {
+                const int r = idx >> 6, c = idx & 63;
+                Bs[r * RS + c] = (r == c) ? 1.0 : 0.0;
+                if (c > r) As[r * RS + c] = 0.0;
+            }
+            __syncthreads();
+            tile_trsm_mma(Bs, As, dinv, linv8, tmpw);
+            for (int idx = tid; idx < TB * TB; idx += CT) {
+                const int r = idx >> 6, c = idx & 63;
+                a.linvT[(size_t)j * TB * TB + idx] = Bs[r * RS + c];
+            }
+            continue;
         } else {
             if (MINB == 1 && i == j + 1) {  // park the pre-solve tile in the upper triangle for the next diagonal tile
                 for (int idx = tid; idx < TB * TB; idx += CT) {
@@ -631,13 +649,12 @@ __global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
         if (j < 0) return;
         const int j0 = j * TB;
         const int c = tid & 63, q = tid >> 6;
-        for (int idx = tid; idx < TB * TB / 2; idx += CT) {
+        for (int idx = tid; idx < TB * TB / 2; idx += CT) {  // Ld <- L_jj^-T (upper triangular)
             const int r = idx >> 5, k2 = (idx & 31) * 2;
-            const double2 v = __ldcg(reinterpret_cast<const double2 *>(a.H + (size_t)(j0 + r) * ld + j0 + k2));
+            const double2 v = __ldcg(reinterpret_cast<const double2 *>(a.linvT + (size_t)j * TB * TB + r * TB + k2));
             Ld[r * (TB + 1) + k2] = v.x;
             Ld[r * (TB + 1) + k2 + 1] = v.y;
         }
-        if (tid < TB) dinvs[tid] = __ldcg(a.dinv + j0 + tid);
         double s = 0.0;
         for (int i = T - 1; i > j; i--) {
             // stage L_ij while x_i may still be in flight
@@ -664,24 +681,19 @@ __global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
         }
         part[q * TB + c] = s;
         __syncthreads();
-        if (tid < 32) {
-            double v0 = __ldcg(a.b + j0 + tid) - (part[tid] + part[TB + tid] + part[2 * TB + tid] + part[3 * TB + tid]);
-            double v1 = __ldcg(a.b + j0 + 32 + tid) - (part[32 + tid] + part[TB + 32 + tid] + part[2 * TB + 32 + tid] + part[3 * TB + 32 + tid]);
-#pragma unroll 4
-            for (int c2 = TB - 1; c2 >= 0; c2--) {
-                const double src = (c2 < 32) ? v0 : v1;
-                const double xc = __shfl_sync(0xffffffffu, src, c2 & 31) * dinvs[c2];
-                // x_r -= L[c2][r] * x_c2 for r < c2
-                if (tid < c2) v0 = fma(-Ld[c2 * (TB + 1) + tid], xc, v0);
-                if (tid + 32 < c2) v1 = fma(-Ld[c2 * (TB + 1) + tid + 32], xc, v1);
-                if (tid == (c2 & 31)) {
-                    if (c2 < 32) v0 = xc; else v1 = xc;
-                }
-            }
-            a.b[j0 + tid] = v0;
-            a.b[j0 + 32 + tid] = v1;
-            if (j0 + tid < a.n) a.dx[j0 + tid] = failed ? 0.0f : (float)v0;
-            if (j0 + 32 + tid < a.n) a.dx[j0 + 32 + tid] = failed ? 0.0f : (float)v1;
+        if (tid < TB) xi[tid] = __ldcg(a.b + j0 + tid) - (part[tid] + part[TB + tid] + part[2 * TB + tid] + part[3 * TB + tid]);
+        __syncthreads();
+        {   // x_j = L_jj^-T v : thread (c, q) sums a quarter of row c, quarters combined through shared memory
+            double acc = 0.0;
+#pragma unroll
+            for (int p = 0; p < 16; p++) acc = fma(Ld[c * (TB + 1) + q * 16 + p], xi[q * 16 + p], acc);
+            part[q * TB + c] = acc;
+        }
+        __syncthreads();
+        if (tid < TB) {
+            const double x = part[tid] + part[TB + tid] + part[2 * TB + tid] + part[3 * TB + tid];
+            a.b[j0 + tid] = x;
+            if (j0 + tid < a.n) a.dx[j0 + tid] = failed ? 0.0f : (float)x;
         }
         publish_flag(a.xflags + j, a.epoch);
     }
@@ -858,7 +870,8 @@ cudaError_t launch_small_solve_batch(double *sys, const long long *prob_hoff, co
 }
 
 cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx, int *scratch,
-                                double *dinv, const double *dampdiag, int epoch, cudaStream_t st, int *launches) {
+                                double *dinv, double *linvT, const double *dampdiag, int epoch, cudaStream_t st,
+                                int *launches) {
     // scratch (ints): [0..1] counters, [2] fail, [16 .. 16+T) xflags, [16+T .. 16+2T) preflags, then (T+1)*T tile flags
     const int T = npad / TB;
     (void)epoch;
@@ -884,6 +897,7 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     a.dx = dx;
     a.dinv = dinv;
     a.dampdiag = dampdiag;
+    a.linvT = linvT;
     const size_t sm = (size_t)(2 * TB * RS + 2 * TB + 32 * 34 + TB * DL + 8 * 96 + 8 * 160) * sizeof(double);
     err = cudaFuncSetAttribute(chol_factor_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (err != cudaSuccess) return err;

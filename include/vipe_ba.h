@@ -121,6 +121,15 @@ typedef struct vipe_ba_options {
     int damp_on_pose_hessian; /* 0: lm scales diag(A - S) (:1176);  1: lm scales diag(A) before the Schur complement (solver.py:161-164) */
     int backsub_all_poses;    /* 0: pose index 0 never reaches dz (:1089, Q4);  1: every free pose does (solver.py:182) */
     const unsigned char *frame_flags; /* DEV [K] or NULL.  bit 0: sensor gate (mode 1); bit 1: disparity of this kx frame fixed */
+    /* The focal length as one more variable, shared by fx and fy: the pinhole case of the backend's optimize_intrinsics
+       (vipe/slam/components/buffer.py:496-498, vipe/slam/maths/retractor.py:51-62, vipe/slam/ba/terms.py:217-228).
+       Needs damp_on_pose_hessian and a single-problem, single-rank plan.  While it is on,
+         - vipe_ba_tensors.intrinsics is UPDATED IN PLACE (fx, fy += focal_jscale * step) every iteration, and
+         - dx_out must hold 6*(t1-t0) + 1 floats: the focal step of the last iteration follows the pose steps. */
+    int optimize_focal;  /* 0 */
+    float focal_jscale;  /* d(intrinsics handed to the kernels)/d(variable): 1/intrinsics_factor = 1/8 in the Python path (terms.py:186) */
+    float focal_lm;      /* LHS_ff += focal_lm * H_ff + focal_ep;  Python path: 1e-6, 1e-6 (buffer.py:496) */
+    float focal_ep;
 } vipe_ba_options;
 void vipe_ba_options_default(vipe_ba_options *opt);
 int vipe_ba_set_options(vipe_ba_plan *plan, const vipe_ba_options *opt);

@@ -142,7 +142,7 @@ def install_stubs():
 
 # ----------------------------------------------------------------------------- bundle_adjustment, restated call by call
 def python_bundle_adjustment(poses, disps, disps_sens, intrinsics_full, target, weight, disp_damping, ii, jj, t0, t1,
-                             n_iters, pose_damping, pose_ep, motion_only, limited_disp, alpha, ht, wd):
+                             n_iters, pose_damping, pose_ep, motion_only, limited_disp, alpha, ht, wd, optimize_intrinsics=False):
     """buffer.py:373-525 for n_views == 1, pinhole, no intrinsics / rig optimisation, no sparse tracks.
     poses[N,7], disps[N,ht,wd] (updated in place), intrinsics_full[1,4] at full resolution (factor 8),
     target/weight[E, ht*wd, 2] channel-last, disp_damping[N,ht,wd]."""
@@ -181,7 +181,8 @@ def python_bundle_adjustment(poses, disps, disps_sens, intrinsics_full, target, 
     solver.set_marginilized("dense_disp")
     solver.set_retractor("intrinsics", IntrinsicsRetractor(CameraType.PINHOLE))
     solver.set_damping("intrinsics", damping=1e-6, ep=1e-6)
-    solver.set_fixed("intrinsics")
+    if not optimize_intrinsics:  # buffer.py:497-498
+        solver.set_fixed("intrinsics")
     solver.set_retractor("rig", RigRotationOnlyRetractor())
     solver.set_damping("rig", damping=1e-4, ep=1e-4)
     solver.set_fixed("rig")
@@ -198,8 +199,17 @@ CASES = {
     "pyba_c2_full": ("c2", {}, dict(motion_only=False, limited_disp=False, t0=1)),
     "pyba_c1_motion": ("c1", {}, dict(motion_only=True, limited_disp=False, t0=1)),
     "pyba_c2_sensor_limited": ("c2", {"sensor_on_even_frames": True}, dict(motion_only=False, limited_disp=True, t0=4)),
+    # backend default (configs/pipeline/default.yaml:26): the focal length is a variable too; it starts 3 % off
+    "pyba_c2_focal": ("c2", {}, dict(motion_only=False, limited_disp=False, t0=1, optimize_intrinsics=True, focal_scale=1.03)),
+    "pyba_c1_focal_motion": ("c1", {}, dict(motion_only=True, limited_disp=False, t0=1, optimize_intrinsics=True, focal_scale=0.98)),
 }
 STRIDE = 16
+
+
+def _start_intrinsics(pr, flags):
+    intr = (pr.intrinsics * 8.0)[None].clone()  # full resolution, buffer.py:413
+    intr[:, :2] *= flags.get("focal_scale", 1.0)
+    return intr
 
 
 def case_inputs(name):
@@ -216,10 +226,11 @@ def case_inputs(name):
     gen = torch.Generator().manual_seed(77)
     disp_damping = 0.01 * torch.nn.functional.softplus(torch.randn(cfg.n_frames, cfg.ht, cfg.wd, generator=gen))
     return pr, dict(poses=pr.poses.clone(), disps=pr.disps.clone(), disps_sens=pr.disps_sens.clone(),
-                    intrinsics_full=(pr.intrinsics * 8.0)[None].clone(), target=target, weight=weight,
+                    intrinsics_full=_start_intrinsics(pr, flags), target=target, weight=weight,
                     disp_damping=disp_damping, ii=pr.ii.clone(), jj=pr.jj.clone(), t0=flags["t0"], t1=cfg.n_frames,
                     n_iters=cfg.iters, pose_damping=cfg.lm, pose_ep=cfg.ep, motion_only=flags["motion_only"],
-                    limited_disp=flags["limited_disp"], alpha=0.001, ht=cfg.ht, wd=cfg.wd)
+                    limited_disp=flags["limited_disp"], alpha=0.001, ht=cfg.ht, wd=cfg.wd,
+                    optimize_intrinsics=flags.get("optimize_intrinsics", False))
 
 
 def main():
@@ -229,7 +240,8 @@ def main():
     for name in CASES:
         pr, kw = case_inputs(name)
         python_bundle_adjustment(**kw)
-        rec = {"poses": kw["poses"].numpy(), "disps_sub": kw["disps"].reshape(pr.cfg.n_frames, -1)[:, ::STRIDE].numpy()}
+        rec = {"poses": kw["poses"].numpy(), "disps_sub": kw["disps"].reshape(pr.cfg.n_frames, -1)[:, ::STRIDE].numpy(),
+               "intrinsics_full": kw["intrinsics_full"].numpy()}
         np.savez_compressed(out_dir / f"{name}.npz", **rec)
         moved = float((kw["poses"] - pr.poses).abs().max())
         print(f"wrote {name}.npz  max pose change {moved:.4f}  disp change {float((kw['disps'] - pr.disps).abs().max()):.4f}")

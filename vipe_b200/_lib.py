@@ -9,7 +9,7 @@ from pathlib import Path
 _SO = Path(__file__).resolve().parent / "lib" / "libvipe_ba.so"
 _lib = None
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Tensors(C.Structure):
@@ -43,6 +43,10 @@ class Options(C.Structure):
         ("damp_on_pose_hessian", C.c_int),
         ("backsub_all_poses", C.c_int),
         ("frame_flags", C.c_void_p),
+        ("optimize_focal", C.c_int),
+        ("focal_jscale", C.c_float),
+        ("focal_lm", C.c_float),
+        ("focal_ep", C.c_float),
     ]
 
 

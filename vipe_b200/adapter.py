@@ -3,8 +3,9 @@
 `bundle_adjustment` mirrors `GraphBuffer.bundle_adjustment` (vipe/slam/components/buffer.py:373-525), which today runs
 the pure-Python sparse solver (`Solver.run_inplace`, vipe/slam/ba/solver.py:117-197).  The reference itself names the
 CUDA kernels as the intended accelerator for that term (vipe/slam/ba/terms.py:160).  Supported: one view, pinhole
-camera, fixed intrinsics and rig, no sparse-track term -- i.e. the frontend (frontend.py:100-115), the inner filler
-(inner_filler.py:110-116) and the backend with `optimize_intrinsics=false`.  Everything else raises.
+camera, fixed rig, no sparse-track term -- i.e. the frontend (frontend.py:100-115), the inner filler
+(inner_filler.py:110-116) and the backend (backend.py:48-72) with or without `optimize_intrinsics` (for a pinhole
+camera that is one extra variable, the focal length, retractor.py:51-62).  Everything else raises.
 
 Differences between the two reference BAs that the adapter maps onto `vipe_ba_options` (SURVEY.md section 8(a')):
   * target / weight arrive channel-last `[E, ht*wd, 2]` (factor_graph.py:292-293);
@@ -16,7 +17,10 @@ Differences between the two reference BAs that the adapter maps onto `vipe_ba_op
     disparities of frames outside `[t0, t1)` (buffer.py:490-491);
   * LM damping scales the pose Hessian's own diagonal, before the Schur complement (solver.py:161-164), and every
     free pose takes part in the back-substitution (the CUDA BA drops pose index 0, geom_kernels.cu:1089);
-  * `dz > 10 -> 0` (retractor.py:41), final `disps.clamp_(min=0.001)` (buffer.py:525), quaternion renormalised.
+  * `dz > 10 -> 0` (retractor.py:41), final `disps.clamp_(min=0.001)` (buffer.py:525), quaternion renormalised;
+  * `optimize_intrinsics`: the focal length (fx and fy move together) joins the reduced system with damping
+    1e-6 / 1e-6 (buffer.py:496-498); its Jacobian is scaled by 1/8 because the BA runs at 1/8 resolution
+    (terms.py:186,224); `intrinsics` is updated in place.
 The reduced system is solved in fp64 Cholesky here; the Python path uses fp32 SuperLU (solver.py:33-44).
 """
 
@@ -37,9 +41,10 @@ def bundle_adjustment(poses, disps, disps_sens, intrinsics, target, weight, disp
                       pose_damping, pose_ep, motion_only, limited_disp, optimize_intrinsics=False,
                       optimize_rig_rotation=False, dense_disp_alpha=0.001, sparse_tracks_enabled=False, n_views=1):
     """poses[N,7], disps[N,ht,wd], disps_sens[N,ht,wd] (all updated/read in place, CUDA fp32); intrinsics[4] at FULL
-    resolution (the Python path scales by 1/8, terms.py:186); target/weight[E, ht*wd, 2]; disp_damping[N,ht,wd]."""
-    if optimize_intrinsics or optimize_rig_rotation or sparse_tracks_enabled or n_views != 1:
-        raise NotImplementedError("vipe_b200.adapter covers the single-view pinhole BA with fixed intrinsics/rig and no sparse tracks")
+    resolution (the Python path scales by 1/8, terms.py:186), updated in place when `optimize_intrinsics`;
+    target/weight[E, ht*wd, 2]; disp_damping[N,ht,wd]."""
+    if optimize_rig_rotation or sparse_tracks_enabled or n_views != 1:
+        raise NotImplementedError("vipe_b200.adapter covers the single-view pinhole BA with a fixed rig and no sparse tracks")
     assert t0 <= t1
     dev = poses.device
     N, ht, wd = disps.shape
@@ -54,7 +59,7 @@ def bundle_adjustment(poses, disps, disps_sens, intrinsics, target, weight, disp
 
     ii_h = ii.detach().to("cpu", torch.int64).contiguous()
     jj_h = jj.detach().to("cpu", torch.int64).contiguous()
-    plan = cached_plan(ii_h, jj_h, N, ht, wd, int(t0), int(t1), tag="python-ba")
+    plan = cached_plan(ii_h, jj_h, N, ht, wd, int(t0), int(t1), tag="python-ba-focal" if optimize_intrinsics else "python-ba")
     kx = plan.kx
     K = plan.K
     # disparity variables exist only for edge sources (di_unique, buffer.py:402); limited_disp fixes those outside the window
@@ -67,10 +72,13 @@ def bundle_adjustment(poses, disps, disps_sens, intrinsics, target, weight, disp
     gate = disps_sens.reshape(N, HW)[kx_d].sum(1) > 0.0  # per-frame gate, buffer.py:472 (no host sync)
     flags = gate.to(torch.uint8) | (fixed.to(dev).to(torch.uint8) << 1)
     plan.set_options(min_depth=0.1, depth_strict=1, alpha=float(dense_disp_alpha), sensor_mode=1, eta_scale=0.2,
-                     eta_bias=2e-7, dz_max=10.0, renorm_quat=1, damp_on_pose_hessian=1, backsub_all_poses=1, frame_flags=flags)
+                     eta_bias=2e-7, dz_max=10.0, renorm_quat=1, damp_on_pose_hessian=1, backsub_all_poses=1, frame_flags=flags,
+                     optimize_focal=int(bool(optimize_intrinsics)), focal_jscale=1.0 / INTRINSICS_FACTOR, focal_lm=1e-6,
+                     focal_ep=1e-6)
     eta = disp_damping.reshape(N, HW)[kx_d].contiguous()
     P = int(t1) - int(t0)
-    dx = torch.zeros(P, 6, dtype=torch.float32, device=dev)
+    dx_all = torch.zeros(6 * P + 1, dtype=torch.float32, device=dev)  # pose steps, then the focal step
+    dx = dx_all[: 6 * P].view(P, 6)
     dz = torch.zeros(K, HW, dtype=torch.float32, device=dev)
     if n_iters > 0 and P > 0:
         with torch.cuda.device(dev):
@@ -79,5 +87,7 @@ def bundle_adjustment(poses, disps, disps_sens, intrinsics, target, weight, disp
             _lib.check(_lib.lib().vipe_ba_run(plan.handle, C.byref(tens), ws.data_ptr(), int(n_iters), float(pose_damping),
                                               float(pose_ep), int(bool(motion_only)), torch.cuda.current_stream(dev).cuda_stream),
                        "vipe_ba_run")
+    if optimize_intrinsics and n_iters > 0 and P > 0:
+        intrinsics.reshape(-1)[:2] = intr[:2] * INTRINSICS_FACTOR  # exact: the factor is a power of two
     disps.clamp_(min=0.001)  # buffer.py:525
     return dx, dz

@@ -48,6 +48,8 @@ struct vipe_ba_plan {
     std::vector<int> pose_slot, pose_row, frame_prob, prob_npad, prob_n, prob_row0;
     std::vector<long long> prob_hoff;
     size_t off_pslot = 0, off_prow = 0, off_fprob = 0, off_phoff = 0, off_pnpad = 0, off_pn = 0, off_prow0 = 0;
+    size_t off_pn_focal = 0, off_fpart = 0, off_ffpart = 0, off_uf = 0;  // focal-length variable
+    int ntile_f = 0;
     std::vector<int64_t> own_lo, own_hi;
     // workspace layout (byte offsets)
     size_t off_kx = 0, off_fptr = 0, off_fedge = 0, off_ejj = 0, off_gbase = 0, off_mbase = 0, idx_bytes = 0;
@@ -83,7 +85,7 @@ struct vipe_ba_plan {
 };
 static constexpr int kMaxProfIters = 64;
 
-extern "C" int vipe_ba_abi_version(void) { return 2; }
+extern "C" int vipe_ba_abi_version(void) { return 3; }
 
 extern "C" void vipe_ba_options_default(vipe_ba_options *o) {
     if (!o) return;
@@ -99,6 +101,10 @@ extern "C" void vipe_ba_options_default(vipe_ba_options *o) {
     o->damp_on_pose_hessian = d.damp_on_pose_hessian;
     o->backsub_all_poses = d.backsub_all_poses;
     o->frame_flags = nullptr;
+    o->optimize_focal = d.optimize_focal;
+    o->focal_jscale = d.focal_jscale;
+    o->focal_lm = d.focal_lm;
+    o->focal_ep = d.focal_ep;
 }
 
 extern "C" int vipe_ba_set_options(vipe_ba_plan *p, const vipe_ba_options *o) {
@@ -115,6 +121,14 @@ extern "C" int vipe_ba_set_options(vipe_ba_plan *p, const vipe_ba_options *o) {
     n.damp_on_pose_hessian = o->damp_on_pose_hessian;
     n.backsub_all_poses = o->backsub_all_poses;
     n.frame_flags = o->frame_flags;
+    n.optimize_focal = o->optimize_focal;
+    n.focal_jscale = o->focal_jscale;
+    n.focal_lm = o->focal_lm;
+    n.focal_ep = o->focal_ep;
+    if (n.optimize_focal) {
+        if (p->C != 1 || p->world != 1) return fail("optimize_focal needs a single-problem, single-rank plan");
+        if (!n.damp_on_pose_hessian) return fail("optimize_focal follows the Python solver: set damp_on_pose_hessian");
+    }
     p->opt = n;
     // captured graphs have the old options baked in
     for (auto &g : p->graphs)
@@ -174,7 +188,9 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
             const int Pc = (int)(t1s[c] - t0s[c]);
             p->prob_row0[c] = row;
             p->prob_n[c] = 6 * Pc;
-            p->prob_npad[c] = std::max(kCholBlock, (6 * Pc + kCholBlock - 1) / kCholBlock * kCholBlock);
+            // a single problem keeps one spare row for the focal-length variable (Options::optimize_focal)
+            const int nmax = 6 * Pc + (C == 1 ? 1 : 0);
+            p->prob_npad[c] = std::max(kCholBlock, (nmax + kCholBlock - 1) / kCholBlock * kCholBlock);
             p->prob_hoff[c] = hoff;
             if (p->prob_npad[c] > p->prob_n[c]) p->any_padding = true;
             if (C > 1 && p->prob_npad[c] > 2 * kCholBlock) {
@@ -306,7 +322,12 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     p->off_pnpad = take(sizeof(int) * C);
     p->off_pn = take(sizeof(int) * C);
     p->off_prow0 = take(sizeof(int) * C);
+    p->off_pn_focal = take(sizeof(int) * C);
     p->idx_bytes = off;
+    p->ntile_f = focal_tiles(p->HW);
+    p->off_fpart = take(sizeof(float) * (size_t)std::max<int64_t>(E, 1) * p->ntile_f * kFocalStride);
+    p->off_ffpart = take(sizeof(float) * (size_t)K * p->ntile_f * 2);
+    p->off_uf = take(sizeof(float) * (size_t)K * p->HW);
     p->off_epart = take(sizeof(float) * (size_t)std::max<int64_t>(E, 1) * p->ntile * kEdgeStride);
     p->off_gpart = take(sizeof(float) * (size_t)std::max<long long>(p->gbase[K], 1));
     p->off_msc = take(sizeof(double) * (size_t)std::max<long long>(p->mbase[K], 1));
@@ -334,6 +355,11 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     std::memcpy(p->blob.data() + p->off_pnpad, p->prob_npad.data(), sizeof(int) * C);
     std::memcpy(p->blob.data() + p->off_pn, p->prob_n.data(), sizeof(int) * C);
     std::memcpy(p->blob.data() + p->off_prow0, p->prob_row0.data(), sizeof(int) * C);
+    {
+        std::vector<int> nf(p->prob_n);
+        for (auto &v : nf) v += 1;
+        std::memcpy(p->blob.data() + p->off_pn_focal, nf.data(), sizeof(int) * C);
+    }
     *out = p;
     return 0;
 }
@@ -408,7 +434,7 @@ static Tables make_tables(const vipe_ba_plan *p, void *ws) {
     tb.frame_prob = (const int *)(w + p->off_fprob);
     tb.prob_hoff = (const long long *)(w + p->off_phoff);
     tb.prob_npad = (const int *)(w + p->off_pnpad);
-    tb.prob_n = (const int *)(w + p->off_pn);
+    tb.prob_n = (const int *)(w + (p->opt.optimize_focal ? p->off_pn_focal : p->off_pn));
     tb.prob_row0 = (const int *)(w + p->off_prow0);
     tb.C = p->C;
     tb.ntile = p->ntile;
@@ -468,9 +494,35 @@ static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void 
     else
         VBA_CUDA(launch_linearize(la, nframes, std::max(p->dmax, 1), motion_only != 0, p->NT, p->PPT, st));
     p->launches++;
+    if (p->opt.optimize_focal) {
+        FocalArgs fa;
+        fa.tb = la.tb;
+        fa.opt = p->opt;
+        fa.poses = t->poses;
+        fa.disps = t->disps;
+        fa.intr = t->intrinsics;
+        fa.targets = t->targets;
+        fa.weights = t->weights;
+        fa.qbuf = la.qbuf;
+        fa.qwbuf = la.qwbuf;
+        fa.fpart = (float *)(w + p->off_fpart);
+        fa.ffpart = (float *)(w + p->off_ffpart);
+        fa.ufbuf = (float *)(w + p->off_uf);
+        fa.ntile_f = p->ntile_f;
+        fa.motion_only = motion_only;
+        VBA_CUDA(launch_focal(fa, nframes, std::max(p->dmax, 1), st));
+        p->launches++;
+    }
     if (mid) VBA_CUDA(cudaEventRecord(mid, st));
 
     ReduceArgs ra;
+    if (p->opt.optimize_focal) {
+        ra.fpart = (const float *)(w + p->off_fpart);
+        ra.ffpart = (const float *)(w + p->off_ffpart);
+        ra.ntile_f = p->ntile_f;
+        ra.focal_row = p->n;
+        ra.focal_lm = p->opt.focal_lm;
+    }
     ra.tb = la.tb;
     ra.poses = t->poses;
     ra.epart = la.epart;
@@ -500,8 +552,12 @@ static int solve_update_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, vo
     int cnt = 0;
     p->epoch++;
     const Tables tbs = make_tables(p, ws);
+    const bool focal = p->opt.optimize_focal != 0;
     if (p->C == 1) {
-        VBA_CUDA(launch_damped_solve(H, b, p->n, p->npad, lm, ep, t->dx_out, scratch, (double *)(w + p->off_dx),
+        // the solver adds ep + lm * diag(A) to every diagonal entry; diag(A) is 0 in the focal row (its LM term went in
+        // with the assembly), so the focal row ends up with focal_ep
+        if (focal) VBA_CUDA(launch_add_scalar(H + (size_t)p->n * p->npad + p->n, (double)p->opt.focal_ep - (double)ep, st));
+        VBA_CUDA(launch_damped_solve(H, b, p->n + (focal ? 1 : 0), p->npad, lm, ep, t->dx_out, scratch, (double *)(w + p->off_dx),
                                      (double *)(w + p->off_dx) + p->npad, p->opt.damp_on_pose_hessian ? b + p->npad : nullptr, p->epoch, st, &cnt));
     } else {  // many small independent problems: one CTA each
         VBA_CUDA(launch_small_solve_batch(H, tbs.prob_hoff, tbs.prob_n, tbs.prob_npad, tbs.prob_row0, p->C, lm, ep, t->dx_out,
@@ -522,10 +578,16 @@ static int solve_update_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, vo
         ba.qwbuf = (const float *)(w + p->off_qw);
         ba.dx = t->dx_out;
         ba.dz_out = t->dz_out;
+        if (focal) {
+            ba.ufbuf = (const float *)(w + p->off_uf);
+            ba.focal_row = p->n;
+        }
         VBA_CUDA(launch_backsub(ba, nframes, std::max(p->dmax, 1), st));
         p->launches++;
     }
-    VBA_CUDA(launch_pose_retr(t->poses, t->dx_out, tbs.pose_row, (int)p->N, p->opt.renorm_quat, st));
+    // with optimize_focal the intrinsics are a variable too: fx, fy are updated in place
+    VBA_CUDA(launch_pose_retr(t->poses, t->dx_out, tbs.pose_row, (int)p->N, p->opt.renorm_quat,
+                              focal ? const_cast<float *>(t->intrinsics) : nullptr, p->n, p->opt.focal_jscale, st));
     p->launches++;
     return 0;
 }

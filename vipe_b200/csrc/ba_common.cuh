@@ -48,6 +48,11 @@ struct Options {
                                    //    the Schur complement (solver.py:161-164)
     int backsub_all_poses = 0;     // 0: EvT6x1 drops pose index 0 (geom_kernels.cu:1089, Q4); 1: every free pose reaches dz (solver.py:182)
     const unsigned char *frame_flags = nullptr;  // DEV [K]: bit 0 sensor gate (mode 1), bit 1 disparity fixed
+    // Focal length as one more variable, shared by fx and fy (pinhole IntrinsicsRetractor, retractor.py:51-62; the
+    // backend's optimize_intrinsics, buffer.py:496-498).  Its row/column borders the reduced camera system.
+    int optimize_focal = 0;
+    float focal_jscale = 1.0f;               // d(intrinsics passed to the kernels)/d(variable) = 1/intrinsics_factor (terms.py:186,224)
+    float focal_lm = 0.0f, focal_ep = 0.0f;  // LHS_ff += focal_lm * H_ff + focal_ep (buffer.py:496, solver.py:161-164)
 };
 
 __device__ __forceinline__ bool depth_valid(float z, const Options &o) { return o.depth_strict ? (z > o.min_depth) : !(z < o.min_depth); }
@@ -78,10 +83,28 @@ struct LinArgs {
     float *qwbuf;  // [K][HW]  Q*w
 };
 
+constexpr int kFocalNT = 256;     // the focal pass tiles a frame into 256-pixel tiles of its own
+constexpr int kFocalStride = 16;  // per-(edge, focal tile) record: J_j^T w J_f (6), J_f^T w J_f, J_f^T w r, sum_px Q u_f u_m (6)
+
+// Focal-length pass (runs after the linearisation when Options::optimize_focal): everything that involves J_f.
+struct FocalArgs {
+    Tables tb;
+    Options opt;
+    const float *poses, *disps, *intr, *targets, *weights;
+    const float *qbuf, *qwbuf;  // from the linearisation
+    float *fpart;               // [E_slots][ntile_f][kFocalStride]
+    float *ffpart;              // [K][ntile_f][2]: sum_px Q u_f^2, sum_px Q w u_f
+    float *ufbuf;               // [K][HW] u_f = sum_edges J_f^T w J_z (the focal/disparity coupling, kept for the back-substitution)
+    int ntile_f, motion_only;
+};
+
 struct ReduceArgs {
     Tables tb;
     const float *poses;
     const float *epart, *gpart;
+    const float *fpart = nullptr, *ffpart = nullptr;  // focal pass partials (null: focal length fixed)
+    int ntile_f = 0, focal_row = 0;
+    float focal_lm = 0.0f;
     double *msc;   // M scratch
     double *hsys;  // per problem: [n*n] row-major lower triangle (+ full diagonal blocks), then b [n], then diag(A) [n]
                    //   (diag(A): the pose Hessian alone, before the Schur complement, for damp_on_pose_hessian)
@@ -96,6 +119,8 @@ struct BackArgs {
     const float *qbuf, *qwbuf;
     const float *dx;  // [P][6] fp32
     float *dz_out;    // [K][HW]
+    const float *ufbuf = nullptr;  // focal/disparity coupling (null: focal length fixed)
+    int focal_row = 0;             // index of the focal step in dx
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -354,7 +354,9 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
     double *T = G + d * 36;     // [d][36]
     double *hs = T + d * 36;    // [d][27]   summed edge records
     double *gv = hs + d * 27;   // [d][6]    g_m
-    int *aj = reinterpret_cast<int *>(gv + d * 6);  // [d]
+    double *fs = gv + d * 6;    // [d][14]   summed focal records   (focal length free only)
+    double *cf = fs + (a.fpart ? d * 14 : 0);  // [d][6]  border column contribution of edge m's target pose
+    int *aj = reinterpret_cast<int *>(cf + (a.fpart ? d * 6 : 0));  // [d]
 
     for (int m = tid; m < d; m += NT) {
         const int e = tb.fedge[s0 + m];
@@ -417,6 +419,41 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
             }
         }
     }
+    // Focal length (one more variable, row/column `focal_row` of the reduced system):
+    //   H(f, j_m) += J_j^T w J_f - sum_px Q u_f u_m,  H(f,f) += (1 + lm_f) J_f^T w J_f - sum_px Q u_f^2,  b(f) += J_f^T w r - sum_px Q w u_f
+    if (a.fpart) {
+        const int nf = a.focal_row, ntf = a.ntile_f;
+        for (int idx = tid; idx < d * 14; idx += NT) {
+            const int m = idx / 14, r = idx - m * 14;
+            double s = 0.0;
+            if (r < 8 || !a.motion_only) {
+                const float *fp = a.fpart + ((size_t)(s0 + m) * ntf) * kFocalStride + r;
+                for (int t = 0; t < ntf; t++) s += (double)fp[(size_t)t * kFocalStride];
+            }
+            fs[idx] = s;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < d * 6; idx += NT) {
+            const int m = idx / 6, r = idx - m * 6;
+            const double c = fs[m * 14 + r] - fs[m * 14 + 8 + r];
+            cf[idx] = c;
+            if (aj[m] >= 0) atomicAdd(hsys + (size_t)nf * n + 6 * aj[m] + r, c);
+        }
+        if (tid == 0) {
+            double hff = 0.0, vf = 0.0, yff = 0.0, sf = 0.0;
+            for (int m = 0; m < d; m++) {  // every edge counts, whether or not its target pose is free
+                hff += fs[m * 14 + 6];
+                vf += fs[m * 14 + 7];
+            }
+            if (!a.motion_only)
+                for (int t = 0; t < ntf; t++) {
+                    yff += (double)a.ffpart[((size_t)k * ntf + t) * 2];
+                    sf += (double)a.ffpart[((size_t)k * ntf + t) * 2 + 1];
+                }
+            atomicAdd(hsys + (size_t)nf * n + nf, hff * (1.0 + (double)a.focal_lm) - yff);
+            atomicAdd(bsys + nf, vf - sf);
+        }
+    }
     if (ai < 0) return;  // source pose fixed: no source rows (uniform over the CTA)
     __syncthreads();
 
@@ -458,6 +495,16 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
             for (int q = 0; q < 6; q++) s += G[m * 36 + r * 6 + q] * gv[m * 6 + q];
         }
         atomicAdd(bsys + 6 * ai + r, s);
+    } else if (tid >= 128 && tid < 134) {
+        if (a.fpart) {  // H(f, i) += sum_m G_m c_m
+            const int r = tid - 128;
+            double s = 0.0;
+            for (int m = 0; m < d; m++) {  // stereo edges have c_m = 0
+#pragma unroll
+                for (int q = 0; q < 6; q++) s += G[m * 36 + r * 6 + q] * cf[m * 6 + q];
+            }
+            atomicAdd(hsys + (size_t)a.focal_row * n + 6 * ai + r, s);
+        }
     } else if (tid >= 96 && tid < 102) {
         // diagonal of sum_m G_m H_jj,m G_m^T alone (the source pose's Hessian before the Schur complement)
         const int r = tid - 96;
@@ -555,6 +602,13 @@ __global__ void __launch_bounds__(NT) backsub_kernel(const BackArgs a) {
             for (int r = 0; r < 6; r++) acc[s] = fmaf(u6[r], y[r], acc[s]);
         }
     }
+    if (a.ufbuf) {  // focal step: dz -= Q u_f df
+        float uf[PPT];
+        load_px<PPT>(a.ufbuf + (size_t)k * HW + px0, uf);
+        const float df = a.dx[a.focal_row];
+#pragma unroll
+        for (int s = 0; s < PPT; s++) acc[s] = fmaf(uf[s], df, acc[s]);
+    }
     float q[PPT], qw[PPT], dz[PPT], hn[PPT];
     load_px<PPT>(a.qbuf + (size_t)k * HW + px0, q);
     load_px<PPT>(a.qwbuf + (size_t)k * HW + px0, qw);
@@ -569,11 +623,137 @@ __global__ void __launch_bounds__(NT) backsub_kernel(const BackArgs a) {
 }
 
 // =================================================================================================
+// Focal pass (optimize_focal): everything that involves J_f = d(projection)/d(focal), for one (frame, 256-pixel tile).
+// With xn = (col - cx)/fx, yn = (row - cy)/fy and X_j = R (xn, yn, 1) + h t:
+//   J_f = jscale * [ X + fx d (g_x - X g_z) ;  Y + fy d (g_y - Y g_z) ],   g = -R (xn/fx, yn/fy, 0)
+// i.e. the target camera's d(proj)/df plus the source camera's d(iproj)/df pushed through the transform
+// (PinholeCameraModel.iproj_disp / proj_points, cameras.py:153-159,201-205; iproj_i_proj_j_disp, geom.py:282-287;
+// both index the same intrinsics row, so the two Jacobians add, terms.py:217-228).
+// Loop 1 (reads targets + weights): per edge J_j^T w J_f (6), J_f^T w J_f, J_f^T w r; per pixel u_f = sum_e J_f^T w J_z.
+// Loop 2 (weights only, full BA): per edge sum_px Q u_f u_m (6); per tile sum_px Q u_f^2, sum_px Q w u_f.
+__global__ void __launch_bounds__(kFocalNT) focal_kernel(const FocalArgs a) {
+    constexpr int NW = kFocalNT / 32;
+    extern __shared__ __align__(16) float smem[];
+    const Tables &tb = a.tb;
+    const int tile = blockIdx.x;
+    const int k = tb.k_lo + blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int src = tb.kx[k];
+    const int s0 = tb.fptr[k];
+    const int d = tb.fptr[k + 1] - s0;
+    if (d == 0) return;
+    const int HW = tb.HW;
+    float *ec = smem;                         // [d][16]
+    float *red = ec + d * kEcStride;          // [d][NW][16]
+    float *red2 = red + d * NW * kFocalStride;  // [NW][2]
+    for (int m = tid; m < d; m += kFocalNT) {
+        const int e = tb.fedge[s0 + m];
+        RelPose<float> rp;
+        relative_pose<float>(a.poses, src, tb.e_jj[e], rp);
+        write_edge_consts(ec + m * kEcStride, rp, e);
+    }
+    for (int idx = tid; idx < d * NW * kFocalStride; idx += kFocalNT) red[idx] = 0.0f;
+    const float fx = __ldg(a.intr + 0), fy = __ldg(a.intr + 1), cx = __ldg(a.intr + 2), cy = __ldg(a.intr + 3);
+    const float js = a.opt.focal_jscale;
+    const int px = tile * kFocalNT + tid;
+    const bool inb = px < HW;
+    const float h = inb ? __ldg(a.disps + (size_t)src * HW + px) : 0.0f;
+    const int row = px / tb.wd, col = px - row * tb.wd;
+    const float xn = __fdiv_rn((float)col - cx, fx), yn = __fdiv_rn((float)row - cy, fy);
+    const float xnf = __fdiv_rn(xn, fx), ynf = __fdiv_rn(yn, fy);
+    __syncthreads();
+
+    float uf = 0.0f;
+    for (int m = 0; m < d; m++) {
+        const float *c = ec + m * kEcStride;
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) v[q] = 0.0f;
+        if (c[12] == 0.0f && inb) {
+            const int e = __float_as_int(c[13]);
+            const size_t base = (size_t)e * 2 * HW + px;
+            const float tu = __ldg(a.targets + base), tv = __ldg(a.targets + base + HW);
+            const float wu = __ldg(a.weights + base), wv = __ldg(a.weights + base + HW);
+            const PixelGeom g = pixel_geom(c, xn, yn, h, fx, fy, a.opt);
+            const float w_u = g.valid ? kWeightScale * wu : 0.0f;
+            const float w_v = g.valid ? kWeightScale * wv : 0.0f;
+            const float ru = (tu - cx) - fx * g.X, rv = (tv - cy) - fy * g.Y;
+            const float gx = -fmaf(c[0], xnf, c[1] * ynf), gy = -fmaf(c[3], xnf, c[4] * ynf), gz = -fmaf(c[6], xnf, c[7] * ynf);
+            const float Jfu = js * fmaf(fx * g.dinv, fmaf(-g.X, gz, gx), g.X);
+            const float Jfv = js * fmaf(fy * g.dinv, fmaf(-g.Y, gz, gy), g.Y);
+            const float XY = g.X * g.Y;
+            const float A0 = fx * g.a, A2 = -g.X * A0, A3 = -fx * XY, A4 = fx * fmaf(g.X, g.X, 1.0f), A5 = -fx * g.Y;
+            const float B1 = fy * g.a, B2 = -g.Y * B1, B3 = -fy * fmaf(g.Y, g.Y, 1.0f), B4 = fy * XY, B5 = fy * g.X;
+            const float pu = w_u * Jfu, pv = w_v * Jfv;
+            v[0] = A0 * pu;
+            v[1] = B1 * pv;
+            v[2] = fmaf(A2, pu, B2 * pv);
+            v[3] = fmaf(A3, pu, B3 * pv);
+            v[4] = fmaf(A4, pu, B4 * pv);
+            v[5] = fmaf(A5, pu, B5 * pv);
+            v[6] = fmaf(pu, Jfu, pv * Jfv);
+            v[7] = fmaf(pu, ru, pv * rv);
+            uf = fmaf(w_u * g.Jzu, Jfu, fmaf(w_v * g.Jzv, Jfv, uf));
+        }
+        const float tot = warp_transpose_reduce<8>(v, lane);
+        if (lane < 8) red[(m * NW + warp) * kFocalStride + lane] = tot;
+    }
+    if (!a.motion_only) {
+        const float q = inb ? __ldg(a.qbuf + (size_t)k * HW + px) : 0.0f;
+        const float qw = inb ? __ldg(a.qwbuf + (size_t)k * HW + px) : 0.0f;
+        if (inb) a.ufbuf[(size_t)k * HW + px] = uf;
+        const float quf = q * uf;
+        float s2[2] = {quf * uf, qw * uf};
+        const float t2 = warp_transpose_reduce<2>(s2, lane);
+        if (lane < 2) red2[warp * 2 + lane] = t2;
+        for (int m = 0; m < d; m++) {
+            const float *c = ec + m * kEcStride;
+            float y[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) y[r] = 0.0f;
+            if (c[12] == 0.0f && inb) {
+                const int e = __float_as_int(c[13]);
+                const size_t base = (size_t)e * 2 * HW + px;
+                const float wu = __ldg(a.weights + base), wv = __ldg(a.weights + base + HW);
+                const PixelGeom g = pixel_geom(c, xn, yn, h, fx, fy, a.opt);
+                const float w_u = g.valid ? kWeightScale * wu : 0.0f;
+                const float w_v = g.valid ? kWeightScale * wv : 0.0f;
+                float u6[6];
+                edge_u(g, w_u * g.Jzu * fx, w_v * g.Jzv * fy, u6);
+#pragma unroll
+                for (int r = 0; r < 6; r++) y[r] = u6[r] * quf;
+            }
+            const float tot = warp_transpose_reduce<8>(y, lane);
+            if (lane < 6) red[(m * NW + warp) * kFocalStride + 8 + lane] = tot;
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < d * 14; idx += kFocalNT) {
+        const int m = idx / 14, r = idx - m * 14;
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < NW; w++) s += red[(m * NW + w) * kFocalStride + r];
+        a.fpart[((size_t)(s0 + m) * a.ntile_f + tile) * kFocalStride + r] = s;
+    }
+    if (!a.motion_only && tid < 2) {
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < NW; w++) s += red2[w * 2 + tid];
+        a.ffpart[((size_t)k * a.ntile_f + tile) * 2 + tid] = s;
+    }
+}
+
+// =================================================================================================
 // Stage 4b: pose retraction T <- exp(xi) T without quaternion renormalisation
 // (pose_retr_kernel / retrSE3 / expSE3 / expSO3, geom_kernels.cu:116-177,882-931).
 __global__ void pose_retr_kernel(float *__restrict__ poses, const float *__restrict__ dx, const int *__restrict__ pose_row,
-                                 int n_poses, int renorm) {
+                                 int n_poses, int renorm, float *intr, int focal_row, float focal_jscale) {
     const int kk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (intr && kk == 0) {  // IntrinsicsRetractor.oplus for a pinhole camera: fx, fy += df (retractor.py:55-60)
+        const float df = dx[focal_row] * focal_jscale;
+        intr[0] += df;
+        intr[1] += df;
+    }
     if (kk >= n_poses) return;
     const int row = pose_row[kk];
     if (row < 0) return;
@@ -683,7 +863,7 @@ cudaError_t launch_linearize(const LinArgs &a, int nframes, int dmax, bool motio
 
 cudaError_t launch_frame_reduce(const ReduceArgs &a, int nframes, int dmax, cudaStream_t st) {
     if (nframes <= 0) return cudaSuccess;
-    const size_t sm = (size_t)dmax * (36 + 36 + 27 + 6) * sizeof(double) + (size_t)dmax * sizeof(int) + 16;
+    const size_t sm = (size_t)dmax * (36 + 36 + 27 + 6 + (a.fpart ? 20 : 0)) * sizeof(double) + (size_t)dmax * sizeof(int) + 16;
     cudaError_t err = cudaFuncSetAttribute(frame_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (err != cudaSuccess) return err;
     frame_reduce_kernel<<<nframes, 256, sm, st>>>(a);
@@ -709,9 +889,28 @@ cudaError_t launch_backsub(const BackArgs &a, int nframes, int dmax, cudaStream_
     return launch_back_t<128, 1>(a, nframes, dmax, st);
 }
 
-cudaError_t launch_pose_retr(float *poses, const float *dx, const int *pose_row, int n_poses, int renorm, cudaStream_t st) {
+cudaError_t launch_pose_retr(float *poses, const float *dx, const int *pose_row, int n_poses, int renorm, float *intr,
+                             int focal_row, float focal_jscale, cudaStream_t st) {
     if (n_poses <= 0) return cudaSuccess;
-    pose_retr_kernel<<<(n_poses + 127) / 128, 128, 0, st>>>(poses, dx, pose_row, n_poses, renorm);
+    pose_retr_kernel<<<(n_poses + 127) / 128, 128, 0, st>>>(poses, dx, pose_row, n_poses, renorm, intr, focal_row, focal_jscale);
+    return cudaGetLastError();
+}
+
+__global__ void add_scalar_kernel(double *p, double v) { *p += v; }
+cudaError_t launch_add_scalar(double *p, double v, cudaStream_t st) {
+    add_scalar_kernel<<<1, 1, 0, st>>>(p, v);
+    return cudaGetLastError();
+}
+
+int focal_tiles(int HW) { return (HW + kFocalNT - 1) / kFocalNT; }
+
+cudaError_t launch_focal(const FocalArgs &a, int nframes, int dmax, cudaStream_t st) {
+    if (nframes <= 0) return cudaSuccess;
+    const size_t sm = ((size_t)dmax * (kEcStride + (kFocalNT / 32) * kFocalStride) + 2 * (kFocalNT / 32)) * sizeof(float) + 16;
+    cudaError_t err = cudaFuncSetAttribute(focal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (err != cudaSuccess) return err;
+    dim3 grid(a.ntile_f, nframes);
+    focal_kernel<<<grid, kFocalNT, sm, st>>>(a);
     return cudaGetLastError();
 }
 

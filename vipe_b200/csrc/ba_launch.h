@@ -16,7 +16,13 @@ bool tile_config2(int HW, int dmax, bool motion, int &NT);
 cudaError_t launch_linearize2(const LinArgs &a, int nframes, int dmax, bool motion, int NT, cudaStream_t st);
 cudaError_t launch_frame_reduce(const ReduceArgs &a, int nframes, int dmax, cudaStream_t st);
 cudaError_t launch_backsub(const BackArgs &a, int nframes, int dmax, cudaStream_t st);
-cudaError_t launch_pose_retr(float *poses, const float *dx, const int *pose_row, int n_poses, int renorm, cudaStream_t st);
+// `intr` non-null: also apply the focal step dx[focal_row] * focal_jscale to fx and fy
+cudaError_t launch_pose_retr(float *poses, const float *dx, const int *pose_row, int n_poses, int renorm, float *intr,
+                             int focal_row, float focal_jscale, cudaStream_t st);
+// focal-length pass (optimize_focal): its own 256-pixel tiling of a frame
+int focal_tiles(int HW);
+cudaError_t launch_add_scalar(double *p, double v, cudaStream_t st);
+cudaError_t launch_focal(const FocalArgs &a, int nframes, int dmax, cudaStream_t st);
 
 // Dense damped Cholesky solve of the reduced camera system (chol.cu).
 //   H: [npad x npad] fp64 row-major, lower triangle valid on entry (destroyed);  b: [npad] fp64 (destroyed)

@@ -294,8 +294,6 @@ def main():
     barrier()
     if batched:
         plans = list(slam_ext._BATCH_PLANS.values())[-1:]  # the plan the warm-up just built
-    for pl in plans:
-        _lib.check(_lib.lib().vipe_ba_profile_enable(pl.handle, 1), "profile_enable")
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -310,26 +308,51 @@ def main():
         ev[s][0].record()
         step()
         ev[s][1].record()
-        if plans:
-            torch.cuda.synchronize()
-            for pl in plans:
-                ms4, its = (C.c_float * 4)(), C.c_int()
-                _lib.check(_lib.lib().vipe_ba_profile_read(pl.handle, C.byref(ms4), C.byref(its)), "profile_read")
-                stage_ms = [x + y for x, y in zip(stage_ms, ms4)]
-                stage_iters += its.value
     barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    launches = sum(pl.launch_count for pl in plans) * args.steps if plans else None
+    # per-stage times come from a separate, untimed pass: stage events switch the CUDA-graph replay off
+    for pl in plans:
+        _lib.check(_lib.lib().vipe_ba_profile_enable(pl.handle, 1), "profile_enable")
+    for s in range(min(args.steps, 5) if plans else 0):
+        reset()
+        flush_buf.zero_()
+        step()
+        torch.cuda.synchronize()
+        for pl in plans:
+            ms4, its = (C.c_float * 4)(), C.c_int()
+            _lib.check(_lib.lib().vipe_ba_profile_read(pl.handle, C.byref(ms4), C.byref(its)), "profile_read")
+            stage_ms = [x + y for x, y in zip(stage_ms, ms4)]
+            stage_iters += its.value
+    # stages 1-2 alone (per-edge Jacobians/Hessians, no Schur Gram): the motion-only variant of the same kernel
+    jac_ms = None
+    if plans and not batched and not cfg.motion_only:
+        tot, its_tot = 0.0, 0
+        for s in range(5):
+            reset()
+            flush_buf.zero_()
+            a = list(dev_args[0])
+            a[11], a[14] = 1, True
+            slam_ext.ba(*a)
+            torch.cuda.synchronize()
+            ms4, its = (C.c_float * 4)(), C.c_int()
+            _lib.check(_lib.lib().vipe_ba_profile_read(plans[0].handle, C.byref(ms4), C.byref(its)), "profile_read")
+            if s > 0:  # the first call compiles nothing but warms the motion-only kernel's instruction cache
+                tot += ms4[0]
+                its_tot += its.value
+        jac_ms = tot / max(its_tot, 1)
+    for pl in plans:
+        _lib.check(_lib.lib().vipe_ba_profile_enable(pl.handle, 0), "profile_enable")
     shard_stage = None
     if sharded:
         evs = shard_prof["events"][-args.steps * cfg.iters:]
         shard_stage = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) / len(evs) for i in range(3)]
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-    launches = sum(pl.launch_count for pl in plans) * args.steps if plans else None
     if sharded:
         # the phased entry points accumulate their launch count in the plan: per step = total / (warm-up + timed steps)
         launches = int(shard_prof["plan"].launch_count * args.steps / (args.steps + args.warmup))
@@ -376,6 +399,12 @@ def main():
                                 "note": "the fused Jacobian+Schur kernel is FMA-bound at backend degrees; see DESIGN.md section 4"},
                     "whole_iteration": {"algorithmic_bytes": it_bytes,
                                         "achieved_gbs": it_bytes * cfg.iters * (clips // nprob if batched else clips) * args.steps / (total_ms * 1e-3) / 1e9 / max(world, 1)}}
+        if jac_ms:
+            _, jac_bytes = algorithmic_bytes(cfg, E, K, N, HW, True)
+            roofline["jacobian_stage_alone"] = {
+                "kernel": "vba::linearize2_kernel<.., MOTION> (stages 1-2 only: projective transform, J_j, per-edge H/v; no Schur Gram)",
+                "avg_launch_ms": jac_ms, "algorithmic_bytes_per_launch": jac_bytes,
+                "achieved": jac_bytes / (jac_ms * 1e-3) / 1e9, "unit": "GB/s", "frac": jac_bytes / (jac_ms * 1e-3) / 1e9 / peak}
         prof = ROOT / "profiles" / "traffic.json"
         if prof.is_file():
             try:

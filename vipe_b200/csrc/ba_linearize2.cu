@@ -48,7 +48,7 @@ __device__ __forceinline__ float group8_transpose_reduce(float (&v)[8], int lane
 // pixels and split its edges (even / odd), which doubles the warps per SM at the same shared-memory footprint
 // (the staging buffer, not registers, bounds occupancy).
 template <int NT, bool MOTION>
-__global__ void __launch_bounds__(2 * NT) linearize2_kernel(const LinArgs a) {
+__global__ void __launch_bounds__(2 * NT, (MOTION && NT == 256) ? 2 : 1) linearize2_kernel(const LinArgs a) {
     constexpr int TILE = NT * 2;
     constexpr int NW = NT / 32;   // warps per half
     constexpr int NTH = 2 * NT;   // threads per CTA

@@ -14,6 +14,9 @@ registered in sys.modules before the import (nothing of the reference is copied)
 The body of `bundle_adjustment` (which lives in a class that needs rerun/GUI imports) is restated below line by
 line for the single-view pinhole case without intrinsics / rig optimisation and without sparse tracks.
 
+Re-running the script reproduces the committed vectors to ~2e-6 only (the Python solver's threaded fp32 sums and
+SuperLU are not bit-reproducible run to run); the tolerances of the tests are 1e-4 / 1e-3.
+
 Usage: python tests/golden/make_python_ba_golden.py
 """
 
@@ -142,7 +145,8 @@ def install_stubs():
 
 # ----------------------------------------------------------------------------- bundle_adjustment, restated call by call
 def python_bundle_adjustment(poses, disps, disps_sens, intrinsics_full, target, weight, disp_damping, ii, jj, t0, t1,
-                             n_iters, pose_damping, pose_ep, motion_only, limited_disp, alpha, ht, wd, optimize_intrinsics=False):
+                             n_iters, pose_damping, pose_ep, motion_only, limited_disp, alpha, ht, wd, optimize_intrinsics=False,
+                             sparse_target=None, sparse_weight=None):
     """buffer.py:373-525 for n_views == 1, pinhole, no intrinsics / rig optimisation, no sparse tracks.
     poses[N,7], disps[N,ht,wd] (updated in place), intrinsics_full[1,4] at full resolution (factor 8),
     target/weight[E, ht*wd, 2] channel-last, disp_damping[N,ht,wd]."""
@@ -163,6 +167,10 @@ def python_bundle_adjustment(poses, disps, disps_sens, intrinsics_full, target, 
     solver.add_term(DenseDepthFlowTerm(pose_i_inds=pi, pose_j_inds=pj, rig_i_inds=qi, rig_j_inds=qj, dense_disp_i_inds=di,
                                        target=target, weight=weight_dense_disp * weight, intrinsics=None,
                                        intrinsics_factor=8.0, rig=None, image_size=(ht, wd), camera_type=CameraType.PINHOLE))
+    if sparse_target is not None:  # the sparse-track flow term: same edges, its own targets and weights (buffer.py:422-449)
+        solver.add_term(DenseDepthFlowTerm(pose_i_inds=pi, pose_j_inds=pj, rig_i_inds=qi, rig_j_inds=qj, dense_disp_i_inds=di,
+                                           target=sparse_target, weight=0.001 * sparse_weight, intrinsics=None,
+                                           intrinsics_factor=8.0, rig=None, image_size=(ht, wd), camera_type=CameraType.PINHOLE))
     solver.set_fixed("pose", torch.cat([pi_unique[pi_unique < t0], pi_unique[pi_unique >= t1]]) if t0 < t1 else None)
     solver.set_retractor("pose", PoseRetractor())
     solver.set_damping("pose", damping=pose_damping, ep=pose_ep)
@@ -202,6 +210,8 @@ CASES = {
     # backend default (configs/pipeline/default.yaml:26): the focal length is a variable too; it starts 3 % off
     "pyba_c2_focal": ("c2", {}, dict(motion_only=False, limited_disp=False, t0=1, optimize_intrinsics=True, focal_scale=1.03)),
     "pyba_c1_focal_motion": ("c1", {}, dict(motion_only=True, limited_disp=False, t0=1, optimize_intrinsics=True, focal_scale=0.98)),
+    # second flow term from sparse tracks: 3 % of the pixels carry a (less noisy) track target with a large weight
+    "pyba_c2_tracks": ("c2", {}, dict(motion_only=False, limited_disp=False, t0=1, sparse_tracks=True)),
 }
 STRIDE = 16
 
@@ -225,7 +235,14 @@ def case_inputs(name):
     weight = pr.weights.reshape(E, 2, HW).permute(0, 2, 1).contiguous()
     gen = torch.Generator().manual_seed(77)
     disp_damping = 0.01 * torch.nn.functional.softplus(torch.randn(cfg.n_frames, cfg.ht, cfg.wd, generator=gen))
-    return pr, dict(poses=pr.poses.clone(), disps=pr.disps.clone(), disps_sens=pr.disps_sens.clone(),
+    sparse = {}
+    if flags.get("sparse_tracks"):
+        g2 = torch.Generator().manual_seed(78)
+        clean = make_problem(cfg_name, noise_px=0.0, **kw).targets.reshape(E, 2, HW).permute(0, 2, 1)
+        sparse["sparse_target"] = (clean + 0.05 * torch.randn(E, HW, 2, generator=g2)).contiguous()
+        hit = (torch.rand(E, HW, 1, generator=g2) < 0.03).float()
+        sparse["sparse_weight"] = (hit * 5.0).expand(E, HW, 2).contiguous()
+    return pr, dict(**sparse, poses=pr.poses.clone(), disps=pr.disps.clone(), disps_sens=pr.disps_sens.clone(),
                     intrinsics_full=_start_intrinsics(pr, flags), target=target, weight=weight,
                     disp_damping=disp_damping, ii=pr.ii.clone(), jj=pr.jj.clone(), t0=flags["t0"], t1=cfg.n_frames,
                     n_iters=cfg.iters, pose_damping=cfg.lm, pose_ep=cfg.ep, motion_only=flags["motion_only"],

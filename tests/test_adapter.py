@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", ["pyba_c1_full", "pyba_c2_full", "pyba_c1_motion", "pyba_c2_sensor_limited", "pyba_c2_focal",
-                                  "pyba_c1_focal_motion"])
+                                  "pyba_c1_focal_motion", "pyba_c2_tracks"])
 def test_adapter_matches_python_ba(lib_built, name):
     import sys
 
@@ -35,7 +35,9 @@ def test_adapter_matches_python_ba(lib_built, name):
     adapter.bundle_adjustment(poses, disps, kw["disps_sens"].to(dev), intr, kw["target"].to(dev),
                               kw["weight"].to(dev), kw["disp_damping"].to(dev), kw["ii"].to(dev), kw["jj"].to(dev), kw["t0"],
                               kw["t1"], kw["n_iters"], kw["pose_damping"], kw["pose_ep"], kw["motion_only"], kw["limited_disp"],
-                              optimize_intrinsics=kw["optimize_intrinsics"], dense_disp_alpha=kw["alpha"])
+                              optimize_intrinsics=kw["optimize_intrinsics"], dense_disp_alpha=kw["alpha"],
+                              sparse_target=kw["sparse_target"].to(dev) if "sparse_target" in kw else None,
+                              sparse_weight=kw["sparse_weight"].to(dev) if "sparse_weight" in kw else None)
     torch.cuda.synchronize()
     gi = torch.from_numpy(g["intrinsics_full"])[0]
     if kw["optimize_intrinsics"]:  # the focal length moved by several pixels; it must land where the Python solver puts it

@@ -3,7 +3,7 @@
 `bundle_adjustment` mirrors `GraphBuffer.bundle_adjustment` (vipe/slam/components/buffer.py:373-525), which today runs
 the pure-Python sparse solver (`Solver.run_inplace`, vipe/slam/ba/solver.py:117-197).  The reference itself names the
 CUDA kernels as the intended accelerator for that term (vipe/slam/ba/terms.py:160).  Supported: one view, pinhole
-camera, fixed rig, no sparse-track term -- i.e. the frontend (frontend.py:100-115), the inner filler
+camera, fixed rig, with or without the sparse-track flow term -- i.e. the frontend (frontend.py:100-115), the inner filler
 (inner_filler.py:110-116) and the backend (backend.py:48-72) with or without `optimize_intrinsics` (for a pinhole
 camera that is one extra variable, the focal length, retractor.py:51-62).  Everything else raises.
 
@@ -39,12 +39,14 @@ INTRINSICS_FACTOR = 8.0  # buffer.py:413
 
 def bundle_adjustment(poses, disps, disps_sens, intrinsics, target, weight, disp_damping, ii, jj, t0, t1, n_iters,
                       pose_damping, pose_ep, motion_only, limited_disp, optimize_intrinsics=False,
-                      optimize_rig_rotation=False, dense_disp_alpha=0.001, sparse_tracks_enabled=False, n_views=1):
+                      optimize_rig_rotation=False, dense_disp_alpha=0.001, sparse_target=None, sparse_weight=None, n_views=1):
     """poses[N,7], disps[N,ht,wd], disps_sens[N,ht,wd] (all updated/read in place, CUDA fp32); intrinsics[4] at FULL
     resolution (the Python path scales by 1/8, terms.py:186), updated in place when `optimize_intrinsics`;
-    target/weight[E, ht*wd, 2]; disp_damping[N,ht,wd]."""
-    if optimize_rig_rotation or sparse_tracks_enabled or n_views != 1:
-        raise NotImplementedError("vipe_b200.adapter covers the single-view pinhole BA with a fixed rig and no sparse tracks")
+    target/weight[E, ht*wd, 2]; disp_damping[N,ht,wd].  `sparse_target/sparse_weight[E, ht*wd, 2]`: the optional second
+    flow term from sparse tracks (what `sparse_tracks.compute_dense_disp_target_weight` returns, buffer.py:422-449): the
+    same edges with their own targets and weights, i.e. E more edges for the kernels."""
+    if optimize_rig_rotation or n_views != 1:
+        raise NotImplementedError("vipe_b200.adapter covers the single-view pinhole BA with a fixed rig")
     assert t0 <= t1
     dev = poses.device
     N, ht, wd = disps.shape
@@ -56,6 +58,13 @@ def bundle_adjustment(poses, disps, disps_sens, intrinsics, target, weight, disp
     tgt = target.reshape(E, ht, wd, 2).permute(0, 3, 1, 2).contiguous()
     wgt = weight.reshape(E, ht, wd, 2).permute(0, 3, 1, 2).contiguous()
     intr = (intrinsics.reshape(-1)[:4] / INTRINSICS_FACTOR).contiguous()
+    if sparse_target is not None:
+        if tuple(sparse_target.shape) != (E, HW, 2) or tuple(sparse_weight.shape) != (E, HW, 2):
+            raise RuntimeError("sparse_target/sparse_weight must be channel-last [E, ht*wd, 2]")
+        # both terms carry the same 0.001 weight factor (buffer.py:396), so the track term is just a second set of edges
+        tgt = torch.cat([tgt, sparse_target.reshape(E, ht, wd, 2).permute(0, 3, 1, 2)]).contiguous()
+        wgt = torch.cat([wgt, sparse_weight.reshape(E, ht, wd, 2).permute(0, 3, 1, 2)]).contiguous()
+        ii, jj = torch.cat([ii, ii]), torch.cat([jj, jj])
 
     ii_h = ii.detach().to("cpu", torch.int64).contiguous()
     jj_h = jj.detach().to("cpu", torch.int64).contiguous()

@@ -287,3 +287,41 @@ def test_batched_clips_match_per_clip_oracle(slam_ext, dev, motion_only):
         else:
             assert disp_error(a[1][c * N:(c + 1) * N], ref[1], tr.bk.kx) <= TOL_D
         assert (dx[c * 7:(c + 1) * 7].cpu().double() - dxr).norm() <= 2e-2 * dxr.norm() + 1e-7
+
+
+def _hub_problem(n_frames, ht=24, wd=32):
+    """Star graph: frame 0 is the source of an edge to every other frame (degree n_frames - 1) and their target."""
+    cfg = BAConfig(f"hub{n_frames}", 300 + n_frames, n_frames, 2 * (n_frames - 1), ht, wd, 2, 1e-4, 0.1, trajectory="orbit")
+    pr = make_problem(cfg)
+    others = torch.arange(1, n_frames)
+    ii = torch.cat([torch.zeros(n_frames - 1, dtype=torch.int64), others])
+    jj = torch.cat([others, torch.zeros(n_frames - 1, dtype=torch.int64)])
+    # targets of the hub edges: the true reprojection of the (perturbed) state is fine for a parity test
+    gen = torch.Generator().manual_seed(n_frames)
+    E = ii.numel()
+    targets = pr.targets[:1].expand(E, -1, -1, -1).clone() + torch.randn(E, 2, ht, wd, generator=gen)
+    weights = torch.rand(E, 2, ht, wd, generator=gen)
+    eta = 0.01 * torch.rand(n_frames, ht, wd, generator=gen) + 1e-6
+
+    def args():
+        return [pr.poses.clone(), pr.disps.clone(), pr.intrinsics.clone(), pr.disps_sens.clone(), targets.clone(), weights.clone(),
+                eta.clone(), ii.clone(), jj.clone(), 1, n_frames, 1, 1e-4, 0.1, False]
+
+    return pr, args
+
+
+@pytest.mark.parametrize("n_frames", [72, 151])
+def test_high_degree_source_frame(slam_ext, dev, n_frames):
+    """A source frame with 71 / 150 outgoing edges: the staging buffer no longer fits the wide tiles, so the plan must
+    fall back to narrower ones (and to the scalar kernel) and still match the oracle."""
+    pr, args = _hub_problem(n_frames)
+    r = _compare(slam_ext, dev, pr, args_cpu=args)
+    assert (r["dx"].cpu().double() - r["dxr"]).norm() <= 1e-4 * r["dxr"].norm(), float((r["dx"].cpu().double() - r["dxr"]).norm() / r["dxr"].norm())
+    assert (r["dz"].cpu().double() - r["dzr"]).norm() <= 1e-3 * r["dzr"].norm()
+
+
+def test_degree_beyond_shared_memory_fails_loudly(slam_ext, dev):
+    pr, args = _hub_problem(900, ht=8, wd=8)
+    a = [x.to(dev) if torch.is_tensor(x) else x for x in args()]
+    with pytest.raises(RuntimeError):
+        slam_ext.ba(*a)

@@ -149,6 +149,23 @@ __device__ __forceinline__ void load_tile_R(double *S, const double *__restrict_
     }
 }
 
+// asynchronous version of load_tile_R (LDGSTS, L2-only caching: the tiles are written by other SMs): the copy of the
+// next k-step's tiles runs under the current step's tensor-core update
+__device__ __forceinline__ void tile_cp_async(double *S, const double *__restrict__ G, int ld) {
+#pragma unroll
+    for (int u = 0; u < TB * TB / 2 / CT; u++) {
+        const int idx = threadIdx.x + u * CT;
+        const int r = idx >> 5, k2 = (idx & 31) * 2;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(S + r * RS + k2);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(G + (size_t)r * ld + k2) : "memory");
+    }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // load a 64x64 tile (global row-major, leading dim ld) into shared memory transposed: S[k][row].
 // All 8 loads of a thread are issued before the first store so that one L2 round trip covers the tile.
 __device__ __forceinline__ void load_tile_T(double *S, const double *__restrict__ G, int ld) {
@@ -451,11 +468,11 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
     double *Bs = sm + TB * RS;   // [64][RS]
     double *col = Bs + TB * RS;  // [64]
     double *dinv = col + TB;     // [64]
-    double *Ltd = dinv + TB;     // [32][34] transposed L11 of the diagonal tile
-    double *Ct = Ltd + 32 * 34;  // [64][DL] the tile being computed
-    double *linv8 = Ct + TB * DL;  // [8][96]
+    double *linv8 = dinv + TB;   // [8][96]
     double *tmpw = linv8 + 8 * 96;  // [8][160]
-    __shared__ int sh_tile, sh_ok;
+    double *As2 = tmpw + 8 * 160;   // second tile pair of the double-buffered k-loop (MINB == 1 only)
+    double *Bs2 = As2 + TB * RS;
+    __shared__ int sh_tile, sh_ok, sh_ready;
     const int T = a.T, ld = a.ld, tid = threadIdx.x;
     const int total = T * (T + 1) / 2 + T;  // lower tiles + one rhs tile per column
 
@@ -546,7 +563,60 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
         }
         TRACE(t, 1);
         // ---- left-looking updates
-        for (int k = 0; k < j; k++) {
+        int kstart = 0;
+        if constexpr (MINB == 1) {
+            // Software-pipelined part of the k-loop (all steps but the diagonal tile's fused last one): the ready flags of
+            // up to 32 steps are polled in one round trip by warp 0, and the tiles of step k+1 are copied asynchronously
+            // into the second buffer pair while the tensor cores work on step k.
+            const int kend = (i == j) ? j - 1 : j;
+            const int lane = tid & 31, warp = tid >> 5;
+            int ready = 0;  // steps k < ready have both of their tiles published
+            auto ensure = [&](int k) {
+                if (k < ready) return;
+                if (warp == 0) {
+                    int r = ready;
+                    for (;;) {
+                        const int kk = r + lane;
+                        bool ok = kk < kend;
+                        if (ok) ok = ld_acquire(a.flags + (size_t)i * T + kk) == a.epoch;
+                        if (ok && i != j) ok = ld_acquire(a.flags + (size_t)j * T + kk) == a.epoch;
+                        const unsigned m = __ballot_sync(0xffffffffu, ok);
+                        r += (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);
+                        if (r > k) break;
+                        __nanosleep(32);
+                    }
+                    if (lane == 0) sh_ready = r;
+                }
+                __syncthreads();
+                ready = sh_ready;
+            };
+            auto issue = [&](int k) {
+                double *Ad = (k & 1) ? As2 : As, *Bd = (k & 1) ? Bs2 : Bs;
+                tile_cp_async(Ad, a.H + (size_t)i0 * ld + k * TB, ld);
+                if (i != j) tile_cp_async(Bd, a.H + (size_t)j0 * ld + k * TB, ld);
+            };
+            if (kend > 0) {
+                ensure(0);
+                issue(0);
+                cp_async_commit();
+            }
+            for (int k = 0; k < kend; k++) {
+                if (k + 1 < kend) {
+                    ensure(k + 1);
+                    issue(k + 1);  // its buffers were last read by step k-1, which ended with a barrier
+                }
+                cp_async_commit();
+                cp_async_wait<1>();
+                __syncthreads();
+                if (k == kend - 1) TRACE(t, 7);
+                const double *Ak = (k & 1) ? As2 : As, *Bk = (k & 1) ? Bs2 : Bs;
+                tile_gemm_sub(acc, Ak, (i != j) ? Bk : Ak);
+                __syncthreads();
+            }
+            cp_async_wait<0>();
+            kstart = kend > 0 ? kend : 0;
+        }
+        for (int k = kstart; k < j; k++) {
             if (MINB == 1 && i == j && k == j - 1) {
                 // Critical path: the diagonal tile's last update needs L_{j,j-1}.  Instead of waiting for the CTA that
                 // owns that tile to solve and publish it (one more trip through L2), take its pre-solve copy -- ready
@@ -898,10 +968,12 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     a.dinv = dinv;
     a.dampdiag = dampdiag;
     a.linvT = linvT;
-    const size_t sm = (size_t)(2 * TB * RS + 2 * TB + 32 * 34 + TB * DL + 8 * 96 + 8 * 160) * sizeof(double);
+    // MINB = 1 double-buffers the tiles of its k-loop (4 tile buffers); MINB = 2 keeps two so that two CTAs fit an SM
+    const size_t sm = (size_t)(4 * TB * RS + 2 * TB + 8 * 96 + 8 * 160) * sizeof(double);
+    const size_t sm2 = (size_t)(2 * TB * RS + 2 * TB + 8 * 96 + 8 * 160) * sizeof(double);
     err = cudaFuncSetAttribute(chol_factor_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (err != cudaSuccess) return err;
-    err = cudaFuncSetAttribute(chol_factor_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    err = cudaFuncSetAttribute(chol_factor_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
     if (err != cudaSuccess) return err;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -911,7 +983,7 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     // large ones are throughput-bound: two CTAs per SM overlap tile loads with the tile GEMMs
     const int ctas = (T >= 400 ? 2 : 1) * sms;
     const int grid = total < ctas ? total : ctas;
-    if (T >= 400) chol_factor_kernel<2><<<grid, CT, sm, st>>>(a);
+    if (T >= 400) chol_factor_kernel<2><<<grid, CT, sm2, st>>>(a);
     else chol_factor_kernel<1><<<grid, CT, sm, st>>>(a);
     const size_t smb = (size_t)(2 * TB * (TB + 1) + 6 * TB) * sizeof(double);
     err = cudaFuncSetAttribute(chol_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);

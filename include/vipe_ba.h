@@ -147,6 +147,18 @@ int vipe_ba_linearize(const vipe_ba_plan *plan, const vipe_ba_tensors *t, void *
                       void *stream);
 int vipe_ba_solve_update(const vipe_ba_plan *plan, const vipe_ba_tensors *t, void *workspace, float lm, float ep,
                          int motion_only, void *stream);
+/*
+ * Multi-GPU without a separate all-reduce (needs NVSwitch multicast memory, e.g. torch symmetric memory):
+ * `accum_local` is this rank's instance of a symmetric buffer of `count_out` doubles (vipe_ba_system_buffer) and
+ * `accum_multicast` the multicast address of the same buffer.  While set, vipe_ba_linearize accumulates this rank's
+ * partial system into `accum_local` instead of the workspace, and vipe_ba_solve_update reads its input THROUGH THE
+ * SWITCH (multimem.ld_reduce: the sum over all ranks' instances) tile by tile as the factorisation reaches it -- the
+ * all-reduce is fused into the Cholesky's loads.  The caller provides the cross-rank barrier between the two calls and
+ * alternates two buffers from iteration to iteration (a rank may start clearing buffer k+2 only after every rank has
+ * finished reading buffer k, which the barrier of iteration k+1 guarantees).  Needs 6*(t1-t0) > 128.  NULL, NULL: off.
+ */
+int vipe_ba_set_peer_system(vipe_ba_plan *plan, double *accum_local, const double *accum_multicast);
+
 /* DEV fp64 buffer holding [H (n x n, row-major, lower triangle valid) ; b (n) ; diag of the pose Hessian (n)],
    n = 6*(t1-t0) rounded up to 64; count_out = n*n + 2n.  This is what a sharded run all-reduces. */
 void *vipe_ba_system_buffer(const vipe_ba_plan *plan, void *workspace, int64_t *n_out, int64_t *count_out);

@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, name, out):
+def _worker(rank, world, port, name, out, collective):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dev = torch.device("cuda", rank)
@@ -23,7 +23,9 @@ def _worker(rank, world, port, name, out):
 
     pr = make_problem(name)
     a = pr.args(dev)
-    dx, dz = ba_sharded(*a)
+    prof = {}
+    dx, dz = ba_sharded(*a, collective=collective, profile=prof)
+    assert prof["collective"] == collective
     torch.cuda.synchronize()
     if rank == 0:
         torch.save({"poses": a[0].cpu(), "disps": a[1].cpu(), "dx": dx.cpu(), "dz": dz.cpu()}, out)
@@ -40,8 +42,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("name", ["c2", "c3"])
-def test_sharded_matches_single_gpu(lib_built, tmp_path, name):
+@pytest.mark.parametrize("name,collective", [("c2", "allreduce"), ("c3", "allreduce"), ("c3", "nvls")])
+def test_sharded_matches_single_gpu(lib_built, tmp_path, name, collective):
+    """"nvls": no all-reduce launch; the Cholesky kernel reads the sum of the ranks' partial systems through the NVSwitch
+    (multimem.ld_reduce), see vipe_b200/distributed.py PeerSystem."""
     world = torch.cuda.device_count()
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -50,7 +54,7 @@ def test_sharded_matches_single_gpu(lib_built, tmp_path, name):
     from vipe_b200.synthetic import disp_error, make_problem, pose_errors
 
     out = tmp_path / "r0.pt"
-    mp.spawn(_worker, args=(world, _free_port(), name, str(out)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), name, str(out), collective), nprocs=world, join=True)
     got = torch.load(out)
     pr = make_problem(name)
     a = pr.args(torch.device("cuda:0"))

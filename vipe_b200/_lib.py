@@ -78,6 +78,7 @@ SIGNATURES = {
     "vipe_ba_debug_q": (C.c_void_p, [C.c_void_p, C.c_void_p]),
     "vipe_ba_debug_qw": (C.c_void_p, [C.c_void_p, C.c_void_p]),
     "vipe_ba_launch_count": (C.c_int64, [C.c_void_p]),
+    "vipe_ba_set_peer_system": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vipe_ba_set_graphs": (C.c_int, [C.c_void_p, C.c_int]),
     "vipe_ba_options_default": (None, [C.POINTER(Options)]),
     "vipe_ba_set_options": (C.c_int, [C.c_void_p, C.POINTER(Options)]),

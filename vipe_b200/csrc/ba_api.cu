@@ -72,6 +72,10 @@ struct vipe_ba_plan {
     mutable cudaStream_t capture_stream = nullptr;
     mutable bool use_graphs = true;
     Options opt;  // semantic switches (vipe_ba_set_options)
+    // multi-GPU fused reduction (vipe_ba_set_peer_system): where this rank accumulates its partial system, and the
+    // multicast address through which the solve reads the sum over ranks
+    mutable double *peer_accum = nullptr;
+    mutable const double *peer_mc = nullptr;
     // optional stage timing
     bool profile = false;
     mutable std::vector<cudaEvent_t> events;  // 5 per iteration
@@ -465,7 +469,7 @@ static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void 
     if (check_tensors(p, t, motion_only)) return 1;
     if (!ws) return fail("null workspace");
     unsigned char *w = (unsigned char *)ws;
-    double *H = (double *)(w + p->off_sys);
+    double *H = p->peer_accum ? p->peer_accum : (double *)(w + p->off_sys);
     double *b = H + (size_t)p->npad * p->npad;
     {
         const Tables t0b = make_tables(p, ws);
@@ -557,8 +561,11 @@ static int solve_update_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, vo
         // the solver adds ep + lm * diag(A) to every diagonal entry; diag(A) is 0 in the focal row (its LM term went in
         // with the assembly), so the focal row ends up with focal_ep
         if (focal) VBA_CUDA(launch_add_scalar(H + (size_t)p->n * p->npad + p->n, (double)p->opt.focal_ep - (double)ep, st));
+        if (p->peer_mc && p->npad <= 2 * kCholBlock)
+            return fail("the fused multi-GPU reduction needs the tiled solver (more than 128 unknowns); use the all-reduce path");
         VBA_CUDA(launch_damped_solve(H, b, p->n + (focal ? 1 : 0), p->npad, lm, ep, t->dx_out, scratch, (double *)(w + p->off_dx),
-                                     (double *)(w + p->off_dx) + p->npad, p->opt.damp_on_pose_hessian ? b + p->npad : nullptr, p->epoch, st, &cnt));
+                                     (double *)(w + p->off_dx) + p->npad, p->opt.damp_on_pose_hessian ? b + p->npad : nullptr,
+                                     p->peer_mc, p->epoch, st, &cnt));
     } else {  // many small independent problems: one CTA each
         VBA_CUDA(launch_small_solve_batch(H, tbs.prob_hoff, tbs.prob_n, tbs.prob_npad, tbs.prob_row0, p->C, lm, ep, t->dx_out,
                                           p->opt.damp_on_pose_hessian != 0, st, &cnt));
@@ -640,6 +647,16 @@ static bool same_args(const vipe_ba_plan::GraphEntry &g, const vipe_ba_tensors *
                       float ep, int motion_only) {
     return std::memcmp(&g.t, t, sizeof(*t)) == 0 && g.ws == ws && g.iterations == iterations && g.lm == lm && g.ep == ep &&
            g.motion_only == motion_only;
+}
+
+extern "C" int vipe_ba_set_peer_system(vipe_ba_plan *p, double *accum_local, const double *accum_multicast) {
+    if (!p) return fail("null plan");
+    if ((accum_local == nullptr) != (accum_multicast == nullptr)) return fail("give both pointers or neither");
+    if (accum_local && p->C != 1) return fail("batched plans are not sharded");
+    if (accum_local && p->opt.optimize_focal) return fail("optimize_focal needs a single-rank plan");
+    p->peer_accum = accum_local;
+    p->peer_mc = accum_multicast;
+    return 0;
 }
 
 extern "C" int vipe_ba_set_graphs(vipe_ba_plan *p, int on) {

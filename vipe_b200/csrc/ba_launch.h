@@ -32,7 +32,9 @@ cudaError_t launch_focal(const FocalArgs &a, int nframes, int dmax, cudaStream_t
 // a value never used before on this scratch (tile ready flags are epoch-valued so they need no per-solve reset).
 cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx, int *scratch,
                                 double *dinv /*[npad]*/, double *linvT /*[npad/64][4096]*/,
-                                const double *dampdiag /*[npad] or null*/, int epoch, cudaStream_t st, int *launches);
+                                const double *dampdiag /*[npad] or null*/,
+                                const double *Ain /*null, or multicast address of the ranks' [H;b;diag(A)] partials*/,
+                                int epoch, cudaStream_t st, int *launches);
 size_t chol_scratch_ints(int npad);
 // zero every problem's [H ; b ; diag(A)] block and put the identity on the padded diagonals
 cudaError_t launch_system_clear(double *sys, size_t total_doubles, const long long *prob_hoff, const int *prob_n,

@@ -95,7 +95,19 @@ struct CholArgs {
     double *dinv;  // [npad] 1 / diag(L)
     const double *dampdiag;  // [npad] or null: lm scales this instead of the matrix's own diagonal
     double *linvT;           // [T][64*64] inverse-transposes of the diagonal tiles (for the backward substitution)
+    // Multi-GPU, optional: multicast address of the ranks' partial systems [H ; b ; diag(A)] (same layout, ld*ld + 2*ld
+    // doubles).  When set, the INPUT of the factorisation is read with multimem.ld_reduce, i.e. summed over the ranks
+    // inside the NVSwitch, tile by tile, as the dataflow reaches it -- the all-reduce of the reduced camera system is
+    // fused into the Cholesky's own loads.  Outputs (L, y, x) still go to the local H / b.
+    const double *Ain;
 };
+
+// one element of the rank-summed input system through the switch (NVLS in-switch reduction)
+__device__ __forceinline__ double mc_load_sum(const double *p) {
+    double v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // Tile GEMM on the fp64 tensor cores (mma.sync.m8n8k4.f64 -> DMMA).  Measured on B200: DMMA issues at the full
 // 64 FMA/clk/SM with one instruction per 256 FMAs, whereas a DFMA outer-product loop fed from shared memory
@@ -523,8 +535,10 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
             __syncthreads();
             if (tid < 32) {
                 // forward substitution by one warp: lane owns entries lane and lane+32
-                double v0 = __ldcg(a.b + j0 + tid) - (As[tid] + As[TB + tid] + As[2 * TB + tid] + As[3 * TB + tid]);
-                double v1 = __ldcg(a.b + j0 + 32 + tid) - (As[32 + tid] + As[TB + 32 + tid] + As[2 * TB + 32 + tid] + As[3 * TB + 32 + tid]);
+                const double b0 = a.Ain ? mc_load_sum(a.Ain + (size_t)ld * ld + j0 + tid) : __ldcg(a.b + j0 + tid);
+                const double b1 = a.Ain ? mc_load_sum(a.Ain + (size_t)ld * ld + j0 + 32 + tid) : __ldcg(a.b + j0 + 32 + tid);
+                double v0 = b0 - (As[tid] + As[TB + tid] + As[2 * TB + tid] + As[3 * TB + tid]);
+                double v1 = b1 - (As[32 + tid] + As[TB + 32 + tid] + As[2 * TB + 32 + tid] + As[3 * TB + 32 + tid]);
                 for (int c2 = 0; c2 < TB; c2++) {
                     const double src = (c2 < 32) ? v0 : v1;
                     const double yc = __shfl_sync(0xffffffffu, src, c2 & 31) * dinv[c2];
@@ -553,11 +567,19 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
 #pragma unroll
             for (int mt = 0; mt < 8; mt++) {
                 const int r = 8 * mt + (lane >> 2), c = 8 * warp + 2 * (lane & 3);
-                const double2 v = __ldcg(reinterpret_cast<const double2 *>(a.H + (size_t)(i0 + r) * ld + j0 + c));
-                acc[mt][0] = v.x, acc[mt][1] = v.y;
-                if (i == j && i0 + r < a.n) {
-                    if (r == c) acc[mt][0] += (double)a.ep + (double)a.lm * (a.dampdiag ? a.dampdiag[i0 + r] : acc[mt][0]);
-                    if (r == c + 1) acc[mt][1] += (double)a.ep + (double)a.lm * (a.dampdiag ? a.dampdiag[i0 + r] : acc[mt][1]);
+                if (a.Ain) {
+                    const double *src = a.Ain + (size_t)(i0 + r) * ld + j0 + c;
+                    acc[mt][0] = mc_load_sum(src);
+                    acc[mt][1] = mc_load_sum(src + 1);
+                } else {
+                    const double2 v = __ldcg(reinterpret_cast<const double2 *>(a.H + (size_t)(i0 + r) * ld + j0 + c));
+                    acc[mt][0] = v.x, acc[mt][1] = v.y;
+                }
+                if (i == j && i0 + r < a.n && (r == c || r == c + 1)) {
+                    const int e = (r == c) ? 0 : 1;
+                    double dd = acc[mt][e];
+                    if (a.dampdiag) dd = a.Ain ? mc_load_sum(a.Ain + (size_t)ld * ld + ld + i0 + r) : a.dampdiag[i0 + r];
+                    acc[mt][e] += (double)a.ep + (double)a.lm * dd;
                 }
             }
         }
@@ -940,12 +962,15 @@ cudaError_t launch_small_solve_batch(double *sys, const long long *prob_hoff, co
 }
 
 cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx, int *scratch,
-                                double *dinv, double *linvT, const double *dampdiag, int epoch, cudaStream_t st,
-                                int *launches) {
+                                double *dinv, double *linvT, const double *dampdiag, const double *Ain, int epoch,
+                                cudaStream_t st, int *launches) {
     // scratch (ints): [0..1] counters, [2] fail, [16 .. 16+T) xflags, [16+T .. 16+2T) preflags, then (T+1)*T tile flags
     const int T = npad / TB;
     (void)epoch;
-    if (T <= 2) return launch_small_solve(H, b, n, npad, lm, ep, dx, dampdiag, st, launches);
+    if (T <= 2) {
+        if (Ain) return cudaErrorNotSupported;  // the fused multi-GPU input needs the tiled solver (callers check)
+        return launch_small_solve(H, b, n, npad, lm, ep, dx, dampdiag, st, launches);
+    }
     // ready flags, counters and the failure flag are reset by one small memset per solve (graph-capturable, and the
     // flags never carry state from one solve to the next)
     cudaError_t err = cudaMemsetAsync(scratch, 0, chol_scratch_ints(npad) * sizeof(int), st);
@@ -968,6 +993,7 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     a.dinv = dinv;
     a.dampdiag = dampdiag;
     a.linvT = linvT;
+    a.Ain = Ain;
     // MINB = 1 double-buffers the tiles of its k-loop (4 tile buffers); MINB = 2 keeps two so that two CTAs fit an SM
     const size_t sm = (size_t)(4 * TB * RS + 2 * TB + 8 * 96 + 8 * 160) * sizeof(double);
     const size_t sm2 = (size_t)(2 * TB * RS + 2 * TB + 8 * 96 + 8 * 160) * sizeof(double);

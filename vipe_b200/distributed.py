@@ -4,7 +4,8 @@ One process per GPU.  Disparities couple only to the edges that leave their own 
 (geom_kernels.cu:292 reads disps[ii]; C, w, E are grouped by `ii`, :1365-1373), so every rank eliminates the
 disparities of the source frames it owns locally and only the reduced camera system
 [H ; b] (fp64, 6P x 6P + 6P) is summed across ranks -- one `all_reduce` per Gauss-Newton iteration over
-NCCL / NVLink.  The damped Cholesky solve is replicated (every rank reduces the same buffer, so every rank
+NCCL / NVLink -- or, where NVSwitch multicast memory is available, no collective at all: the Cholesky kernel reads the
+sum over the ranks' partial systems through the switch (`collective="nvls"`).  The damped Cholesky solve is replicated (every rank reduces the same buffer, so every rank
 computes the same dx), back-substitution and disparity retraction are local to the owner, and the owned
 disparity rows are exchanged once per call, not per iteration.
 
@@ -22,6 +23,49 @@ import torch.distributed as dist
 from . import _lib
 from .ext import slam_ext
 from .plan import cached_plan
+
+
+class PeerSystem:
+    """Two instances of the reduced camera system [H ; b ; diag(A)] in NVSwitch multicast (symmetric) memory.
+
+    With them the per-iteration all-reduce disappears: every rank accumulates its partial system into its own
+    instance, one cross-rank barrier follows, and the Cholesky kernel of every rank loads its input with
+    `multimem.ld_reduce` -- the sum over the ranks' instances, formed inside the switch, tile by tile as the
+    factorisation gets there (include/vipe_ba.h: vipe_ba_set_peer_system).  torch supplies the plumbing only:
+    the symmetric allocation, the rendezvous that maps the multicast address, and the barrier."""
+
+    def __init__(self, plan, dev, group):
+        import torch.distributed._symmetric_memory as symm
+
+        _, npad = plan.system_view(plan.workspace(dev))
+        count = npad * npad + 2 * npad
+        self.bufs = [symm.empty(count, dtype=torch.float64, device=dev) for _ in range(2)]
+        for b in self.bufs:
+            b.zero_()
+        g = group if group is not None else dist.group.WORLD
+        self.hdls = [symm.rendezvous(b, g) for b in self.bufs]
+        if not all(h.multicast_ptr for h in self.hdls):
+            raise RuntimeError("no multicast (NVLS) support on this system")
+        self.k = 0  # iterations so far, over all calls: the buffer parity must never restart (see vipe_ba.h)
+
+    @staticmethod
+    def get(plan, dev, group):
+        key = ("peer", dev.index, None if group is None else id(group))
+        cache = plan.__dict__.setdefault("_peer_systems", {})
+        if key not in cache:
+            cache[key] = PeerSystem(plan, dev, group)
+        return cache[key]
+
+
+def nvls_available(plan, dev, group) -> bool:
+    """The fused reduction needs multicast memory and the tiled solver (more than 128 unknowns)."""
+    if 6 * plan.P <= 128:
+        return False
+    try:
+        PeerSystem.get(plan, dev, group)
+        return True
+    except Exception:
+        return False
 
 
 class CudaShardEngine:
@@ -46,6 +90,9 @@ class CudaShardEngine:
                                                 int(self.motion_only), self._stream()), "vipe_ba_linearize")
         return self.system
 
+    def use_peer_buffer(self, local_ptr, multicast_ptr):
+        _lib.check(_lib.lib().vipe_ba_set_peer_system(self.plan.handle, local_ptr, multicast_ptr), "vipe_ba_set_peer_system")
+
     def solve_update(self, lm: float, ep: float):
         _lib.check(_lib.lib().vipe_ba_solve_update(self.plan.handle, C.byref(self.tens), self.ws.data_ptr(), float(lm),
                                                    float(ep), int(self.motion_only), self._stream()),
@@ -53,8 +100,12 @@ class CudaShardEngine:
 
 
 def ba_sharded(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, t1, iterations, lm, ep,
-               motion_only, group=None, engine_cls=CudaShardEngine, exchange=True, profile=None):
+               motion_only, group=None, engine_cls=CudaShardEngine, exchange=True, profile=None, collective="auto"):
     """`slam_ext.ba` sharded by source keyframe across the ranks of `group`.
+
+    `collective`: "allreduce" = one NCCL all-reduce of the reduced camera system per iteration; "nvls" = no collective
+    launch at all, the sum is formed by the NVSwitch inside the Cholesky kernel's loads (PeerSystem above); "auto" =
+    "nvls" where it is available (CUDA engine, multicast memory, more than 128 unknowns), else "allreduce".
 
     Every rank passes the full tensors (poses are replicated; for targets/weights only the rows of owned edges are
     read).  On return `poses` is identical on all ranks and, if `exchange`, so are `disps[kx]` and `dz`.
@@ -68,24 +119,41 @@ def ba_sharded(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, 
     plan = cached_plan(ii.detach().to("cpu", torch.int64).contiguous(), jj.detach().to("cpu", torch.int64).contiguous(),
                        N, ht, wd, t0, t1, rank, world)
     eng = engine_cls(plan, poses, disps, intrinsics, disps_sens, targets, weights, eta, motion_only)
+    peer = None
+    if world > 1 and engine_cls is CudaShardEngine and collective in ("auto", "nvls"):
+        if nvls_available(plan, poses.device, group):
+            peer = PeerSystem.get(plan, poses.device, group)
+        elif collective == "nvls":
+            raise RuntimeError("collective='nvls' needs NVSwitch multicast memory and more than 128 unknowns")
     if profile is not None:
         profile["plan"] = plan
+        profile["collective"] = "nvls" if peer is not None else "allreduce"
         ev = profile.setdefault("events", [])
-    for _ in range(int(iterations)):
-        if profile is not None:
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            e[0].record()
-        system = eng.linearize()
-        if profile is not None:
-            e[1].record()
-        if world > 1:
-            dist.all_reduce(system, op=dist.ReduceOp.SUM, group=group)
-        if profile is not None:
-            e[2].record()
-        eng.solve_update(lm, ep)
-        if profile is not None:
-            e[3].record()
-            ev.append(e)
+    try:
+        for _ in range(int(iterations)):
+            if profile is not None:
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                e[0].record()
+            if peer is not None:
+                b = peer.k & 1
+                eng.use_peer_buffer(peer.bufs[b].data_ptr(), peer.hdls[b].multicast_ptr)
+                peer.k += 1
+            system = eng.linearize()
+            if profile is not None:
+                e[1].record()
+            if peer is not None:
+                peer.hdls[0].barrier(channel=0)  # every rank's partial system is complete and visible
+            elif world > 1:
+                dist.all_reduce(system, op=dist.ReduceOp.SUM, group=group)
+            if profile is not None:
+                e[2].record()
+            eng.solve_update(lm, ep)
+            if profile is not None:
+                e[3].record()
+                ev.append(e)
+    finally:
+        if peer is not None:
+            eng.use_peer_buffer(None, None)
     if exchange and world > 1 and not motion_only:
         exchange_owned_rows(plan, disps, eng.dz, group)
     return [eng.dx, eng.dz]

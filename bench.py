@@ -210,6 +210,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="auto", choices=["auto", "nvls", "allreduce"],
+                    help="N > 1: how the ranks' partial reduced systems are summed (vipe_b200/distributed.py)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -277,7 +279,7 @@ def main():
     def step():
         for a in dev_args:
             if sharded:
-                ba_sharded(*a, exchange=True, profile=shard_prof)
+                ba_sharded(*a, exchange=True, profile=shard_prof, collective=args.collective)
             elif batched:
                 slam_ext.ba_batch(*a)
             else:
@@ -383,6 +385,9 @@ def main():
         roofline = {"bound": "hbm", "kernel": "vba::linearize2_kernel on rank 0's shard (linearise+Schur+assemble stage)",
                     "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "algorithmic_bytes_per_launch": own_bytes, "avg_launch_ms": lin_ms,
+                    "collective": ("none: the Cholesky kernel sums the ranks' partial systems through the NVSwitch (multimem.ld_reduce); "
+                                   "'all_reduce' below is the cross-rank barrier" if shard_prof.get("collective") == "nvls"
+                                   else "NCCL all_reduce of the reduced camera system"),
                     "stage_ms_per_iteration": {"linearize_schur_assemble": shard_stage[0], "all_reduce": shard_stage[1],
                                                "solve_backsub_retract": shard_stage[2]}}
     elif stage_iters > 0:
@@ -456,7 +461,7 @@ def main():
                 "edge_pixels_per_sec": value * edge_px,
                 "config": {"workload": workload_name(cfg), "frames": N, "edges": E, "ht": cfg.ht, "wd": cfg.wd,
                            "gn_iterations_per_step": cfg.iters, "lm": cfg.lm, "ep": cfg.ep, "motion_only": cfg.motion_only,
-                           "clips": clips, "parallelism": f"keyframe-sharded x{world}" if sharded else ("clips batched per rank, no collective" if clips > 1 else "single"),
+                           "clips": clips, "parallelism": (f"keyframe-sharded x{world}, " + ("in-switch reduction fused into the solve (NVLS)" if shard_prof.get("collective") == "nvls" else "NCCL all-reduce per iteration")) if sharded else ("clips batched per rank, no collective" if clips > 1 else "single"),
                            "l2": "flushed between timed steps (256 MB write)", "timing": "cuda events per step, max over ranks",
                            "wall_s_timed_region": wall},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -32,21 +32,41 @@ class PeerSystem:
     instance, one cross-rank barrier follows, and the Cholesky kernel of every rank loads its input with
     `multimem.ld_reduce` -- the sum over the ranks' instances, formed inside the switch, tile by tile as the
     factorisation gets there (include/vipe_ba.h: vipe_ba_set_peer_system).  torch supplies the plumbing only:
-    the symmetric allocation, the rendezvous that maps the multicast address, and the barrier."""
+    the symmetric allocation, the rendezvous that maps the multicast address, and the barrier.
+
+    Construction is collective and every step is agreed on by all ranks before the next one (a rank that cannot
+    allocate must not leave the others waiting in the rendezvous); `ok` is the same on every rank."""
 
     def __init__(self, plan, dev, group):
-        import torch.distributed._symmetric_memory as symm
-
-        _, npad = plan.system_view(plan.workspace(dev))
-        count = npad * npad + 2 * npad
-        self.bufs = [symm.empty(count, dtype=torch.float64, device=dev) for _ in range(2)]
-        for b in self.bufs:
-            b.zero_()
         g = group if group is not None else dist.group.WORLD
-        self.hdls = [symm.rendezvous(b, g) for b in self.bufs]
-        if not all(h.multicast_ptr for h in self.hdls):
-            raise RuntimeError("no multicast (NVLS) support on this system")
-        self.k = 0  # iterations so far, over all calls: the buffer parity must never restart (see vipe_ba.h)
+        self.ok, self.k = False, 0  # k: iterations so far, over all calls -- the buffer parity never restarts (vipe_ba.h)
+        self.bufs, self.hdls = [], []
+
+        def all_agree(flag: bool) -> bool:
+            t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=g)
+            return bool(t.item())
+
+        symm = None
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            _, npad = plan.system_view(plan.workspace(dev))
+            count = npad * npad + 2 * npad
+            self.bufs = [symm.empty(count, dtype=torch.float64, device=dev) for _ in range(2)]
+            for b in self.bufs:
+                b.zero_()
+            good = True
+        except Exception:
+            good = False
+        if not all_agree(good):
+            return
+        try:
+            self.hdls = [symm.rendezvous(b, g) for b in self.bufs]
+            good = all(h.multicast_ptr for h in self.hdls)
+        except Exception:
+            good = False
+        self.ok = all_agree(good)
 
     @staticmethod
     def get(plan, dev, group):
@@ -58,14 +78,9 @@ class PeerSystem:
 
 
 def nvls_available(plan, dev, group) -> bool:
-    """The fused reduction needs multicast memory and the tiled solver (more than 128 unknowns)."""
-    if 6 * plan.P <= 128:
-        return False
-    try:
-        PeerSystem.get(plan, dev, group)
-        return True
-    except Exception:
-        return False
+    """The fused reduction needs multicast memory and the tiled solver (more than 128 unknowns).  Collective: every
+    rank gets the same answer."""
+    return 6 * plan.P > 128 and PeerSystem.get(plan, dev, group).ok
 
 
 class CudaShardEngine:

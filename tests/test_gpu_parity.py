@@ -325,3 +325,15 @@ def test_degree_beyond_shared_memory_fails_loudly(slam_ext, dev):
     a = [x.to(dev) if torch.is_tensor(x) else x for x in args()]
     with pytest.raises(RuntimeError):
         slam_ext.ba(*a)
+
+
+def test_identity_plan_cache_sees_in_place_edits(slam_ext, dev):
+    """The identity shortcut in front of the plan cache must notice an edge list edited in place."""
+    pr = make_problem("c1")
+    a = pr.args(dev)
+    p1 = slam_ext.ba_plan(a[7], a[8], 8, 48, 64, 1, 8)
+    assert slam_ext.ba_plan(a[7], a[8], 8, 48, 64, 1, 8) is p1
+    a[8][0] = (int(a[8][0]) + 3) % 8  # in-place edit: version counter moves
+    p2 = slam_ext.ba_plan(a[7], a[8], 8, 48, 64, 1, 8)
+    assert p2 is not p1
+    assert slam_ext.ba_plan(a[7].clone(), a[8].clone(), 8, 48, 64, 1, 8) is p2  # same content, other objects: hash cache

@@ -31,10 +31,31 @@ def _check_dtype(dtype, **tensors):
             raise RuntimeError(f"expected scalar type {dtype} for {name} but found {t.dtype}")
 
 
+# Identity cache in front of the content-hashed plan cache: SLAM calls BA several times in a row with the very same
+# `ii` / `jj` tensor objects (every GRU step of FactorGraph.update, vipe/slam/components/factor_graph.py:296).  If the
+# objects are the ones seen last time (weak references still alive, hence not a recycled address) and their version
+# counters have not moved (no in-place write through torch since), the edge list is unchanged and the device-to-host
+# copy + hash -- a stream synchronisation per call -- can be skipped.
+_LAST_PLAN: dict = {}
+
+
 def ba_plan(ii: torch.Tensor, jj: torch.Tensor, n_frames: int, ht: int, wd: int, t0: int, t1: int) -> BAPlan:
     """Build (or fetch from the cache) the index bookkeeping for a graph; `ba` does this implicitly."""
-    return cached_plan(ii.detach().to("cpu", torch.int64).contiguous(), jj.detach().to("cpu", torch.int64).contiguous(),
+    import weakref
+
+    key = (int(n_frames), int(ht), int(wd), int(t0), int(t1))
+    hit = _LAST_PLAN.get("entry")
+    if hit is not None:
+        r_ii, r_jj, v_ii, v_jj, k, plan = hit
+        if r_ii() is ii and r_jj() is jj and ii._version == v_ii and jj._version == v_jj and k == key:
+            return plan
+    plan = cached_plan(ii.detach().to("cpu", torch.int64).contiguous(), jj.detach().to("cpu", torch.int64).contiguous(),
                        n_frames, ht, wd, t0, t1)
+    try:
+        _LAST_PLAN["entry"] = (weakref.ref(ii), weakref.ref(jj), ii._version, jj._version, key, plan)
+    except TypeError:
+        _LAST_PLAN.pop("entry", None)
+    return plan
 
 
 def _tensors(poses, disps, intrinsics, disps_sens, targets, weights, eta, dx, dz, motion_only):

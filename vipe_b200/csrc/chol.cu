@@ -797,13 +797,14 @@ __global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
 // everything resident in shared memory: no ready flags, no hops through L2, one launch.
 //   [A00 .  ]   potrf(A00) -> L10 = A10 L00^-T -> A11 -= L10 L10^T -> potrf(A11) -> two triangular solves
 //   [A10 A11]
+template <int S>
 __device__ void smem_trsv_fwd(const double *L, const double *dinv, double *v, int lane) {
-    // L row-major [64][DL]; solves L y = v in place (one warp)
+    // L row-major [64][S]; solves L y = v in place (one warp)
     double v0 = v[lane], v1 = v[lane + 32];
     for (int c = 0; c < TB; c++) {
         const double yc = __shfl_sync(0xffffffffu, (c < 32) ? v0 : v1, c & 31) * dinv[c];
-        if (lane > c) v0 = fma(-L[lane * DL + c], yc, v0);
-        if (lane + 32 > c) v1 = fma(-L[(lane + 32) * DL + c], yc, v1);
+        if (lane > c) v0 = fma(-L[lane * S + c], yc, v0);
+        if (lane + 32 > c) v1 = fma(-L[(lane + 32) * S + c], yc, v1);
         if (lane == (c & 31)) {
             if (c < 32) v0 = yc; else v1 = yc;
         }
@@ -811,13 +812,14 @@ __device__ void smem_trsv_fwd(const double *L, const double *dinv, double *v, in
     v[lane] = v0;
     v[lane + 32] = v1;
 }
+template <int S>
 __device__ void smem_trsv_bwd(const double *L, const double *dinv, double *v, int lane) {
     // solves L^T x = v in place (one warp)
     double v0 = v[lane], v1 = v[lane + 32];
     for (int c = TB - 1; c >= 0; c--) {
         const double xc = __shfl_sync(0xffffffffu, (c < 32) ? v0 : v1, c & 31) * dinv[c];
-        if (lane < c) v0 = fma(-L[c * DL + lane], xc, v0);
-        if (lane + 32 < c) v1 = fma(-L[c * DL + lane + 32], xc, v1);
+        if (lane < c) v0 = fma(-L[c * S + lane], xc, v0);
+        if (lane + 32 < c) v1 = fma(-L[c * S + lane + 32], xc, v1);
         if (lane == (c & 31)) {
             if (c < 32) v0 = xc; else v1 = xc;
         }
@@ -826,6 +828,8 @@ __device__ void smem_trsv_bwd(const double *L, const double *dinv, double *v, in
     v[lane + 32] = v1;
 }
 
+// Systems of at most two tiles (frontend windows, inner filler: 6P <= 128) entirely in shared memory, one CTA, with the
+// same tensor-core tile kernels as the dataflow solver.
 // Batched form: blockIdx.x selects the problem when `prob_hoff` is non-null (many small independent problems, e.g.
 // 64 motion-only clips); otherwise the explicit H / b / n / ld arguments describe the one problem.
 __global__ void __launch_bounds__(CT) chol_small_kernel(const double *__restrict__ H, const double *__restrict__ b, int n,
@@ -845,15 +849,15 @@ __global__ void __launch_bounds__(CT) chol_small_kernel(const double *__restrict
         dampdiag = damp_on_A ? b + ld : nullptr;
         dx = dx + 6 * (size_t)prob_row0[c];
     }
-    double *A00 = sm;                   // [64][DL]
-    double *A10 = A00 + TB * DL;        // [64][DL]
-    double *A11 = A10 + TB * DL;        // [64][DL]
-    double *Lt = A11 + TB * DL;         // [64][LD]  L00 transposed ([c][q]) for the tile solve
-    double *dinv0 = Lt + TB * LD;       // [64]
+    double *A00 = sm;                   // [64][RS]
+    double *A10 = A00 + TB * RS;        // [64][RS]
+    double *A11 = A10 + TB * RS;        // [64][RS]
+    double *dinv0 = A11 + TB * RS;      // [64]
     double *dinv1 = dinv0 + TB;         // [64]
     double *col = dinv1 + TB;           // [64]
-    double *Ltd = col + TB;             // [32][34]
-    double *rhs = Ltd + 32 * 34;        // [128]
+    double *linv8 = col + TB;           // [8][96]
+    double *tmpw = linv8 + 8 * 96;      // [8][160]
+    double *rhs = tmpw + 8 * 160;       // [128]
     __shared__ int sh_ok;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) sh_ok = 1;
@@ -861,87 +865,81 @@ __global__ void __launch_bounds__(CT) chol_small_kernel(const double *__restrict
         const int r = idx >> 6, c = idx & 63;
         double v = (c <= r) ? H[(size_t)r * ld + c] : 0.0;
         if (r == c && r < n) v += (double)ep + (double)lm * (dampdiag ? dampdiag[r] : v);  // geom_kernels.cu:1176
-        A00[r * DL + c] = v;
+        A00[r * RS + c] = v;
         if (T == 2) {
-            A10[r * DL + c] = H[(size_t)(TB + r) * ld + c];
+            A10[r * RS + c] = H[(size_t)(TB + r) * ld + c];
             double w = (c <= r) ? H[(size_t)(TB + r) * ld + TB + c] : 0.0;
             if (r == c && TB + r < n) w += (double)ep + (double)lm * (dampdiag ? dampdiag[TB + r] : w);
-            A11[r * DL + c] = w;
+            A11[r * RS + c] = w;
         }
     }
     for (int i = tid; i < T * TB; i += CT) rhs[i] = b[i];
     __syncthreads();
-    bool ok = tile_potrf(A00, dinv0, col, Ltd, &sh_ok);
+    bool ok = tile_potrf_mma(A00, dinv0, col, linv8, tmpw, &sh_ok);
     if (T == 2) {
-        for (int idx = tid; idx < TB * TB; idx += CT) {
-            const int r = idx >> 6, c = idx & 63;
-            Lt[c * LD + r] = (c <= r) ? A00[r * DL + c] : 0.0;
-        }
+        tile_trsm_mma(A10, A00, dinv0, linv8, tmpw);  // L10 = A10 L00^-T
         __syncthreads();
-        tile_trsm(A10, Lt, dinv0);
-        {   // A11 -= L10 L10^T (lower part is enough)
-            const int r0 = (tid >> 4) * 4, c0 = (tid & 15) * 4;
-            double acc[4][4];
+        {   // A11 -= L10 L10^T on the tensor cores
+            double acc[8][2];
 #pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int q = 0; q < 4; q++) acc[a][q] = 0.0;
-            if (c0 <= r0 + 3) {
-#pragma unroll 4
-                for (int k = 0; k < TB; k++) {
-                    double av[4], bv[4];
-#pragma unroll
-                    for (int a = 0; a < 4; a++) av[a] = A10[(r0 + a) * DL + k];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) bv[q] = A10[(c0 + q) * DL + k];
-#pragma unroll
-                    for (int a = 0; a < 4; a++)
-#pragma unroll
-                        for (int q = 0; q < 4; q++) acc[a][q] = fma(av[a], bv[q], acc[a][q]);
-                }
-#pragma unroll
-                for (int a = 0; a < 4; a++)
-#pragma unroll
-                    for (int q = 0; q < 4; q++) A11[(r0 + a) * DL + c0 + q] -= acc[a][q];
+            for (int mt = 0; mt < 8; mt++) {
+                const double2 v = *reinterpret_cast<const double2 *>(A11 + (8 * mt + (lane >> 2)) * RS + 8 * warp + 2 * (lane & 3));
+                acc[mt][0] = v.x, acc[mt][1] = v.y;
             }
+            tile_gemm_sub(acc, A10, A10);
+            __syncthreads();
+            acc_to_smem_rs(acc, A11);
         }
         __syncthreads();
-        ok = tile_potrf(A11, dinv1, col, Ltd, &sh_ok) && ok;
+        if (n - TB <= 32) {
+            // at most 32 real rows in the second tile: the rest is the identity padding (its rows of L10 are zero), so only
+            // the leading 32x32 block needs factorising -- half of the pivot chain
+            if (warp == 0) {
+                const bool ok1 = warp_potrf32_smem(A11, dinv1, col);
+                if (!ok1 && lane == 0) sh_ok = 0;
+            } else if (warp == 1) {
+                dinv1[32 + lane] = 1.0;
+            }
+            __syncthreads();
+            ok = (sh_ok != 0) && ok;
+        } else {
+            ok = tile_potrf_mma(A11, dinv1, col, linv8, tmpw, &sh_ok) && ok;
+        }
     }
     if (!ok) {  // failed factorisation => zero update (geom_kernels.cu:1186-1188)
         for (int i = tid; i < n; i += CT) dx[i] = 0.0f;
         return;
     }
     // forward: y0 = L00^-1 b0 ; y1 = L11^-1 (b1 - L10 y0)
-    if (warp == 0) smem_trsv_fwd(A00, dinv0, rhs, lane);
+    if (warp == 0) smem_trsv_fwd<RS>(A00, dinv0, rhs, lane);
     __syncthreads();
     if (T == 2) {
         if (tid < TB) {
             double s = 0.0;
-            for (int k = 0; k < TB; k++) s = fma(A10[tid * DL + k], rhs[k], s);
+            for (int k = 0; k < TB; k++) s = fma(A10[tid * RS + k], rhs[k], s);
             rhs[TB + tid] -= s;
         }
         __syncthreads();
         if (warp == 0) {
-            smem_trsv_fwd(A11, dinv1, rhs + TB, lane);
-            smem_trsv_bwd(A11, dinv1, rhs + TB, lane);
+            smem_trsv_fwd<RS>(A11, dinv1, rhs + TB, lane);
+            smem_trsv_bwd<RS>(A11, dinv1, rhs + TB, lane);
         }
         __syncthreads();
         if (tid < TB) {
             double s = 0.0;
-            for (int k = 0; k < TB; k++) s = fma(A10[k * DL + tid], rhs[TB + k], s);
+            for (int k = 0; k < TB; k++) s = fma(A10[k * RS + tid], rhs[TB + k], s);
             rhs[tid] -= s;
         }
         __syncthreads();
     }
-    if (warp == 0) smem_trsv_bwd(A00, dinv0, rhs, lane);
+    if (warp == 0) smem_trsv_bwd<RS>(A00, dinv0, rhs, lane);
     __syncthreads();
     for (int i = tid; i < n; i += CT) dx[i] = (float)rhs[i];
 }
 
 static cudaError_t launch_small_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx,
                                       const double *dampdiag, cudaStream_t st, int *launches) {
-    const size_t sm = (size_t)(3 * TB * DL + TB * LD + 3 * TB + 32 * 34 + 2 * TB) * sizeof(double);
+    const size_t sm = (size_t)(3 * TB * RS + 3 * TB + 8 * 96 + 8 * 160 + 2 * TB) * sizeof(double);
     cudaError_t err = cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (err != cudaSuccess) return err;
     chol_small_kernel<<<1, CT, sm, st>>>(H, b, n, npad, npad / TB, lm, ep, dx, dampdiag, nullptr, nullptr, nullptr, nullptr, 0);
@@ -952,7 +950,7 @@ static cudaError_t launch_small_solve(double *H, double *b, int n, int npad, flo
 cudaError_t launch_small_solve_batch(double *sys, const long long *prob_hoff, const int *prob_n, const int *prob_npad,
                                      const int *prob_row0, int n_prob, float lm, float ep, float *dx, bool damp_on_A,
                                      cudaStream_t st, int *launches) {
-    const size_t sm = (size_t)(3 * TB * DL + TB * LD + 3 * TB + 32 * 34 + 2 * TB) * sizeof(double);
+    const size_t sm = (size_t)(3 * TB * RS + 3 * TB + 8 * 96 + 8 * 160 + 2 * TB) * sizeof(double);
     cudaError_t err = cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (err != cudaSuccess) return err;
     chol_small_kernel<<<n_prob, CT, sm, st>>>(sys, nullptr, 0, 0, 0, lm, ep, dx, nullptr, prob_hoff, prob_n, prob_npad,

@@ -45,37 +45,36 @@ __device__ __forceinline__ void potrf32_variant(double (&a)[32], double *colbuf,
 // ---- micro timing of the tile primitives (single CTA), cycles via clock64
 __global__ void __launch_bounds__(CT) micro_kernel(double *out, long long *clk) {
     extern __shared__ __align__(16) double sm[];
-    double *As = sm, *Bs = sm + TB * RS, *col = Bs + TB * RS, *dinv = col + TB, *Ltd = dinv + TB;
+    double *As = sm, *Bs = sm + TB * RS, *col = Bs + TB * RS, *dinv = col + TB, *linv8 = dinv + TB, *tmpw = linv8 + 8 * 96;
     __shared__ int sh_ok;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // SPD tile in As (row-major DL)
-    for (int idx = tid; idx < TB * TB; idx += CT) {
-        const int r = idx >> 6, c = idx & 63;
-        As[r * DL + c] = (r == c) ? 100.0 + r : 1.0 / (1 + abs(r - c));
-        Bs[r * DL + c] = 0.5 + 0.001 * idx;
-    }
-    if (tid == 0) sh_ok = 1;
-    __syncthreads();
+    auto fill = [&]() {
+        for (int idx = tid; idx < TB * TB; idx += CT) {
+            const int r = idx >> 6, c = idx & 63;
+            As[r * RS + c] = (r == c) ? 100.0 + r : 1.0 / (1 + abs(r - c));
+            Bs[r * RS + c] = 0.5 + 0.001 * idx;
+        }
+        if (tid == 0) sh_ok = 1;
+        __syncthreads();
+    };
+    fill();
+    tile_potrf_mma(As, dinv, col, linv8, tmpw, &sh_ok);  // warm the instruction cache
+    fill();
     long long t0 = clock64();
-    tile_potrf(As, dinv, col, Ltd, &sh_ok);
+    tile_potrf_mma(As, dinv, col, linv8, tmpw, &sh_ok);
     long long t1 = clock64();
     // warp-level pieces alone
     double a[32];
-    long long t2 = 0, t3 = 0, t4 = 0;
     if (warp == 0) {
-        for (int c = 0; c < 32; c++) a[c] = (lane == c) ? 100.0 + c : 1.0 / (1 + abs(lane - c));
         double inv;
-        long long tt[5];
 #pragma unroll 1
         for (int rep = 0; rep < 4; rep++) {
             for (int c = 0; c < 32; c++) a[c] = (lane == c) ? 100.0 + c + rep : 1.0 / (1 + abs(lane - c));
-            tt[rep] = clock64();
+            const long long q0 = clock64();
             warp_potrf32(a, col, lane, inv);
-            tt[rep + 1] = clock64();
-            if (lane == 0) clk[8 + rep] = tt[rep + 1] - tt[rep];
+            const long long q1 = clock64();
+            if (lane == 0) clk[8 + rep] = q1 - q0;
         }
-        t2 = tt[3];
-        t3 = tt[4];
 #define TIME_VARIANT(V)                                                                        \
         for (int rep = 0; rep < 3; rep++) {                                                    \
             for (int c = 0; c < 32; c++) a[c] = (lane == c) ? 100.0 + c + rep : 1.0 / (1 + abs(lane - c)); \
@@ -86,44 +85,41 @@ __global__ void __launch_bounds__(CT) micro_kernel(double *out, long long *clk) 
             out[lane] += a[lane & 31];                                                         \
         }
         TIME_VARIANT(0) TIME_VARIANT(1) TIME_VARIANT(2) TIME_VARIANT(3) TIME_VARIANT(4)
-        warp_trsm32<34>(a, Ltd, dinv);
-        t4 = clock64();
         out[lane] = a[lane & 31] + inv;
     }
     __syncthreads();
-    // transposed L for tile_trsm: reuse As as if it were Lt (values irrelevant for timing)
-    long long t5 = clock64();
-    tile_trsm(Bs, As, dinv);
-    long long t6 = clock64();
+    long long t2 = clock64();
+    tile_trsm_mma(Bs, As, dinv, linv8, tmpw);
+    __syncthreads();
+    long long t3 = clock64();
     double acc[8][2];
     for (int r = 0; r < 8; r++) for (int c = 0; c < 2; c++) acc[r][c] = r + c;
     __syncthreads();
-    long long t7 = clock64();
+    long long t4 = clock64();
     tile_gemm_sub(acc, As, Bs);
     __syncthreads();
-    long long t8 = clock64();
+    long long t5 = clock64();
     if (tid == 0) {
-        clk[0] = t1 - t0; clk[1] = t3 - t2; clk[2] = t4 - t3; clk[3] = t6 - t5; clk[4] = t8 - t7;
+        clk[0] = t1 - t0; clk[1] = t3 - t2; clk[2] = t5 - t4;
     }
     out[64 + tid] = acc[0][0] + acc[7][1] + Bs[tid];
 }
 
 int main(int argc, char **argv) {
     if (argc > 1 && atoi(argv[1]) == 0) {
-        double *out; long long *clk, h[5];
+        double *out; long long *clk;
         cudaMalloc(&out, 4096 * 8); cudaMalloc(&clk, 256);
-        const size_t smb = (size_t)(2 * TB * RS + 2 * TB + 32 * 34 + TB * DL) * sizeof(double);
+        cudaMemset(out, 0, 4096 * 8);
+        const size_t smb = (size_t)(2 * TB * RS + 2 * TB + 8 * 96 + 8 * 160) * sizeof(double);
         cudaFuncSetAttribute(micro_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
         for (int r = 0; r < 3; r++) {
             micro_kernel<<<1, CT, smb>>>(out, clk);
             cudaDeviceSynchronize();
-            long long h2[4];
-            cudaMemcpy(h, clk, 40, cudaMemcpyDeviceToHost);
-            cudaMemcpy(h2, clk + 8, 32, cudaMemcpyDeviceToHost);
-            printf("warp_potrf32 repeated in a loop: %lld %lld %lld %lld\n", h2[0], h2[1], h2[2], h2[3]);
-            long long h3[5]; cudaMemcpy(h3, clk + 16, 40, cudaMemcpyDeviceToHost);
-            printf("variants (warm): full %lld | rsqrt seed only %lld | no rsqrt %lld | no pivot shuffle %lld | no column exchange %lld\n", h3[0], h3[1], h3[2], h3[3], h3[4]);
-            printf("cycles: tile_potrf64 %lld | warp_potrf32 %lld | warp_trsm32 %lld | tile_trsm64 %lld | tile_gemm_sub %lld   (%s)\n", h[0], h[1], h[2], h[3], h[4], cudaGetErrorString(cudaGetLastError()));
+            long long h[24];
+            cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
+            printf("warp_potrf32 repeated in a loop: %lld %lld %lld %lld\n", h[8], h[9], h[10], h[11]);
+            printf("variants (warm): full %lld | rsqrt seed only %lld | no rsqrt %lld | no pivot shuffle %lld | no column exchange %lld\n", h[16], h[17], h[18], h[19], h[20]);
+            printf("cycles: tile_potrf_mma (64x64) %lld | tile_trsm_mma %lld | tile_gemm_sub %lld   (%s)\n", h[0], h[1], h[2], cudaGetErrorString(cudaGetLastError()));
         }
         return 0;
     }

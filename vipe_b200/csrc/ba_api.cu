@@ -470,7 +470,6 @@ static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void 
     if (!ws) return fail("null workspace");
     unsigned char *w = (unsigned char *)ws;
     double *H = p->peer_accum ? p->peer_accum : (double *)(w + p->off_sys);
-    double *b = H + (size_t)p->npad * p->npad;
     {
         const Tables t0b = make_tables(p, ws);
         VBA_CUDA(launch_system_clear(H, p->sys_doubles, t0b.prob_hoff, t0b.prob_n, t0b.prob_npad, p->C, p->any_padding, st));

@@ -17,7 +17,6 @@ namespace vba {
 constexpr int TB = kCholBlock;  // 64
 constexpr int LD = TB + 2;      // 66: keeps 16-byte alignment of 4-double groups in the [k][row] layout
 constexpr int CT = 256;         // threads per CTA
-constexpr int DL = TB + 1;      // row stride of row-major tiles in shared memory (conflict-free column access)
 
 // ------------------------------------------------------------------------------------------------
 __global__ void pad_identity_kernel(double *sys, const long long *prob_hoff, const int *prob_n, const int *prob_npad) {
@@ -130,17 +129,6 @@ __device__ __forceinline__ void tile_gemm_sub(double (&acc)[8][2], const double 
         const double bneg = -bp[k0];
 #pragma unroll
         for (int mt = 0; mt < 8; mt++) dmma884(acc[mt], ap[mt * 8 * RS + k0], bneg);
-    }
-}
-
-// fragment-distributed tile (acc) -> row-major shared tile S[64][DL]
-__device__ __forceinline__ void acc_to_smem(const double (&acc)[8][2], double *S) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int mt = 0; mt < 8; mt++) {
-        double *d = S + (8 * mt + (lane >> 2)) * DL + 8 * warp + 2 * (lane & 3);
-        d[0] = acc[mt][0];
-        d[1] = acc[mt][1];
     }
 }
 
@@ -257,20 +245,6 @@ __device__ __noinline__ bool warp_potrf32_smem(double *Dblk, double *dinv_out, d
     return ok;
 }
 
-// Warp-level X = A L^-T for a 32x32 block: lane r holds row r of A in registers; L (lower) is read from shared
-// memory TRANSPOSED, Lt[c * ldt + q] = L[q][c] (so that vectorised broadcast loads pair up independent updates),
-// dinv[c] = 1 / L[c][c].
-template <int LDT>
-__device__ __forceinline__ void warp_trsm32(double (&a)[32], const double *Lt, const double *dinv) {
-#pragma unroll
-    for (int c = 0; c < 32; c++) {
-        const double x = a[c] * dinv[c];
-        a[c] = x;
-#pragma unroll
-        for (int q = c + 1; q < 32; q++) a[q] = fma(-x, Lt[c * LDT + q], a[q]);
-    }
-}
-
 __device__ __noinline__ void tile_trsm_mma(double *X, const double *L, const double *dinv, double *linv8, double *tmp, int nblk, int nrw);
 
 // Tensor-core version of tile_potrf for tiles stored with row stride RS: potrf32 (warp 0, registers) ->
@@ -311,105 +285,6 @@ __device__ bool tile_potrf_mma(double *D, double *dinv, double *colbuf, double *
     }
     __syncthreads();
     return *sh_ok != 0;
-}
-
-// D[64][DL] (row-major, shared): factorise the lower triangle in place, write 1/diag to dinv[64].
-// 2x2 blocking: potrf32 (warp 0) -> trsm32 (warp 1) -> syrk (all) -> potrf32 (warp 0).  All threads must call.
-__device__ bool tile_potrf(double *D, double *dinv, double *colbuf, double *Lt, int *sh_ok) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double a[32];
-    if (warp == 0) {
-#pragma unroll
-        for (int c = 0; c < 32; c++) a[c] = D[lane * DL + c];
-        double my_inv;
-        const bool ok = warp_potrf32(a, colbuf, lane, my_inv);
-#pragma unroll
-        for (int c = 0; c < 32; c++) {
-            D[lane * DL + c] = a[c];
-            Lt[c * 34 + lane] = a[c];
-        }
-        dinv[lane] = my_inv;
-        if (!ok && lane == 0) *sh_ok = 0;
-    }
-    __syncthreads();
-    if (warp == 1) {
-#pragma unroll
-        for (int c = 0; c < 32; c++) a[c] = D[(32 + lane) * DL + c];
-        warp_trsm32<34>(a, Lt, dinv);
-#pragma unroll
-        for (int c = 0; c < 32; c++) D[(32 + lane) * DL + c] = a[c];
-    }
-    __syncthreads();
-    {   // A22 -= L21 L21^T : thread -> 2x2 outputs
-        const int r0 = 32 + (tid >> 4) * 2, c0 = 32 + (tid & 15) * 2;
-        double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
-#pragma unroll 8
-        for (int k = 0; k < 32; k++) {
-            const double x0 = D[r0 * DL + k], x1 = D[(r0 + 1) * DL + k];
-            const double y0 = D[c0 * DL + k], y1 = D[(c0 + 1) * DL + k];
-            s00 = fma(x0, y0, s00), s01 = fma(x0, y1, s01), s10 = fma(x1, y0, s10), s11 = fma(x1, y1, s11);
-        }
-        __syncthreads();
-        D[r0 * DL + c0] -= s00, D[r0 * DL + c0 + 1] -= s01, D[(r0 + 1) * DL + c0] -= s10, D[(r0 + 1) * DL + c0 + 1] -= s11;
-    }
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll
-        for (int c = 0; c < 32; c++) a[c] = D[(32 + lane) * DL + 32 + c];
-        double my_inv;
-        const bool ok = warp_potrf32(a, colbuf, lane, my_inv);
-#pragma unroll
-        for (int c = 0; c < 32; c++) D[(32 + lane) * DL + 32 + c] = a[c];
-        dinv[32 + lane] = my_inv;
-        if (!ok && lane == 0) *sh_ok = 0;
-    }
-    __syncthreads();
-    return *sh_ok != 0;
-}
-
-// X[64][DL] (row-major, shared) <- X L^-T; L is given transposed, Lt[c * LD + q] = L[q][c] (load_tile_T layout),
-// dinv[64] = 1 / diag(L).  All threads must call.
-__device__ __noinline__ void tile_trsm(double *X, const double *Lt, const double *dinv) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double a[32];
-    if (warp < 2) {  // X1 = A1 L11^-T, one row per lane
-        const int r = warp * 32 + lane;
-#pragma unroll
-        for (int c = 0; c < 32; c++) a[c] = X[r * DL + c];
-        warp_trsm32<LD>(a, Lt, dinv);
-#pragma unroll
-        for (int c = 0; c < 32; c++) X[r * DL + c] = a[c];
-    }
-    __syncthreads();
-    {   // A2 -= X1 L21^T : 64x32 outputs, K = 32; thread -> 2 rows x 4 cols
-        const int r0 = (tid >> 3) * 2, c0 = 32 + (tid & 7) * 4;
-        double s[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-#pragma unroll 8
-        for (int k = 0; k < 32; k++) {
-            const double x0 = X[r0 * DL + k], x1 = X[(r0 + 1) * DL + k];
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const double l = Lt[k * LD + c0 + b];
-                s[0][b] = fma(x0, l, s[0][b]);
-                s[1][b] = fma(x1, l, s[1][b]);
-            }
-        }
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            X[r0 * DL + c0 + b] -= s[0][b];
-            X[(r0 + 1) * DL + c0 + b] -= s[1][b];
-        }
-    }
-    __syncthreads();
-    if (warp < 2) {  // X2 = A2 L22^-T
-        const int r = warp * 32 + lane;
-#pragma unroll
-        for (int c = 0; c < 32; c++) a[c] = X[r * DL + 32 + c];
-        warp_trsm32<LD>(a, Lt + 32 * LD + 32, dinv + 32);
-#pragma unroll
-        for (int c = 0; c < 32; c++) X[r * DL + 32 + c] = a[c];
-    }
-    __syncthreads();
 }
 
 // X <- X L^-T on the fp64 tensor cores.  X[64][RS] and L[64][RS] (lower, row-major) live in shared memory.
@@ -729,7 +604,6 @@ __global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
     double *Ls = Ld + TB * (TB + 1);     // [64][65] L_ij being applied
     double *part = Ls + TB * (TB + 1);   // [4][64]
     double *xi = part + 4 * TB;          // [64]
-    double *dinvs = xi + TB;             // [64]
     __shared__ int sh_j;
     const int T = a.T, ld = a.ld, tid = threadIdx.x;
     const bool failed = *a.fail != 0;

@@ -10,6 +10,8 @@
 // kernel does the backward substitution.  Claim order respects the dependencies, so every spin-wait is on a tile
 // that a resident CTA is already working on: no cooperative launch is needed.
 // A non-positive (or NaN) pivot raises *fail and the solve writes dx = 0, like the reference (:1186-1188).
+#include <type_traits>
+
 #include "ba_launch.h"
 
 namespace vba {
@@ -56,10 +58,9 @@ __device__ __forceinline__ void wait_flag(const int *f, int epoch) {
 // all threads call after their global writes
 __device__ __forceinline__ void publish_flag(int *f, int epoch) {
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        st_release(f, epoch);
-    }
+    // st.release.gpu is cumulative over everything ordered before it by the barrier; an extra __threadfence() here
+    // compiled to a second (sequentially consistent) MEMBAR on the critical path of every tile
+    if (threadIdx.x == 0) st_release(f, epoch);
 }
 
 #ifdef VBA_CHOL_TRACE
@@ -108,28 +109,53 @@ __device__ __forceinline__ double mc_load_sum(const double *p) {
     return v;
 }
 
-// Tile GEMM on the fp64 tensor cores (mma.sync.m8n8k4.f64 -> DMMA).  Measured on B200: DMMA issues at the full
-// 64 FMA/clk/SM with one instruction per 256 FMAs, whereas a DFMA outer-product loop fed from shared memory
-// sustains only 26-28 FMA/clk/SM (operand delivery), so the trailing updates of the factorisation use DMMA.
+// Tile GEMM on the fp64 tensor cores (mma.sync.m8n8k4.f64 -> DMMA).  Measured on B200 (scripts/dmma_lat.cu): one DMMA
+// (256 FMA) issues every 16 clk per SM sub-partition, i.e. 64 FMA/clk/SM, a dependent DMMA follows after 32-42 clk; a
+// DFMA outer-product loop fed from shared memory sustains only 26-28 FMA/clk/SM (operand delivery), so the trailing
+// updates of the factorisation use DMMA.  A 64x64x64 tile product is 4096 clk of tensor pipe per SM.
 //   acc -= A * B^T, A = L_ik and B = L_jk as ROW-MAJOR tiles in shared memory with row stride RS = 68 doubles
 //   (68 = 4 mod 16 makes both fragment loads conflict-free: lane l reads [l/4][k0 + l%4]).
-// Warp w owns output columns 8w..8w+7 and all 64 rows: 8 accumulator fragments; the C fragment of m-tile mt holds
-// rows 8mt + l/4, columns 8w + 2(l%4) + {0,1}.
+// A warp owns output column block cw (columns 8cw..8cw+7) and the row blocks mt >= mt0: 8 accumulator fragments; the
+// C fragment of row block mt holds rows 8mt + l/4, columns 8cw + 2(l%4) + {0,1}.
+//   off-diagonal tiles: cw = warp, mt0 = 0.
+//   diagonal tiles (symmetric, only the lower blocks are ever read): cw = diag_col(warp), mt0 = cw.  Column c has 8 - c
+//   lower blocks; the tensor pipe belongs to the sub-partition, which hosts warps s and s+4, so giving those two
+//   warps columns s and 7-s loads every pipe with 9 blocks instead of 16: 0.56 of the time of the full update.
 constexpr int RS = 68;
+__device__ __forceinline__ int diag_col(int warp) { return warp < 4 ? warp : 11 - warp; }
 __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
 }
-__device__ __forceinline__ void tile_gemm_sub(double (&acc)[8][2], const double *As, const double *Bs) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double *ap = As + (lane >> 2) * RS + (lane & 3);
-    const double *bp = Bs + (8 * warp + (lane >> 2)) * RS + (lane & 3);
+template <int MT0>
+__device__ __forceinline__ void tile_gemm_sub_from(double (&acc)[8][2], const double *ap, const double *bp) {
 #pragma unroll 4
     for (int k0 = 0; k0 < TB; k0 += 4) {
         const double bneg = -bp[k0];
 #pragma unroll
-        for (int mt = 0; mt < 8; mt++) dmma884(acc[mt], ap[mt * 8 * RS + k0], bneg);
+        for (int mt = MT0; mt < 8; mt++) dmma884(acc[mt], ap[mt * 8 * RS + k0], bneg);
     }
+}
+__device__ __forceinline__ void tile_gemm_sub(double (&acc)[8][2], const double *As, const double *Bs, int cw, int mt0) {
+    const int lane = threadIdx.x & 31;
+    const double *ap = As + (lane >> 2) * RS + (lane & 3);
+    const double *bp = Bs + (8 * cw + (lane >> 2)) * RS + (lane & 3);
+    // a branch per first row block, not a predicate per DMMA: a predicated-off DMMA still holds the tensor pipe (measured:
+    // the predicated form of the lower-blocks-only update took exactly as long as the full one)
+    switch (mt0) {
+        case 0: tile_gemm_sub_from<0>(acc, ap, bp); break;
+        case 1: tile_gemm_sub_from<1>(acc, ap, bp); break;
+        case 2: tile_gemm_sub_from<2>(acc, ap, bp); break;
+        case 3: tile_gemm_sub_from<3>(acc, ap, bp); break;
+        case 4: tile_gemm_sub_from<4>(acc, ap, bp); break;
+        case 5: tile_gemm_sub_from<5>(acc, ap, bp); break;
+        case 6: tile_gemm_sub_from<6>(acc, ap, bp); break;
+        default: tile_gemm_sub_from<7>(acc, ap, bp); break;
+    }
+}
+__device__ __forceinline__ void tile_gemm_sub(double (&acc)[8][2], const double *As, const double *Bs) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    tile_gemm_sub_from<0>(acc, As + (lane >> 2) * RS + (lane & 3), Bs + (8 * warp + (lane >> 2)) * RS + (lane & 3));
 }
 
 // load a 64x64 tile (global row-major, leading dim ld) into shared memory row-major with stride RS
@@ -245,7 +271,8 @@ __device__ __noinline__ bool warp_potrf32_smem(double *Dblk, double *dinv_out, d
     return ok;
 }
 
-__device__ __noinline__ void tile_trsm_mma(double *X, const double *L, const double *dinv, double *linv8, double *tmp, int nblk, int nrw);
+template <int NBLK>
+__device__ __noinline__ void tile_trsm_mma_t(double *X, const double *L, const double *dinv, double *linv8, double *tmp);
 
 // Tensor-core version of tile_potrf for tiles stored with row stride RS: potrf32 (warp 0, registers) ->
 // L21 = A21 L11^-T (DMMA) -> A22 -= L21 L21^T (DMMA) -> potrf32.  All threads must call.
@@ -256,7 +283,7 @@ __device__ bool tile_potrf_mma(double *D, double *dinv, double *colbuf, double *
         if (!ok && lane == 0) *sh_ok = 0;
     }
     __syncthreads();
-    tile_trsm_mma(D + 32 * RS, D, dinv, linv8, tmp, 4, 4);  // rows 32..63, columns 0..31
+    tile_trsm_mma_t<4>(D + 32 * RS, D, dinv, linv8, tmp);  // rows 32..63, columns 0..31
     if (warp < 4) {  // A22 -= L21 L21^T: warp w -> columns 32+8w.., 4 row tiles
         const int fr = lane >> 2, fk = lane & 3;
         double acc[4][2];
@@ -267,16 +294,21 @@ __device__ bool tile_potrf_mma(double *D, double *dinv, double *colbuf, double *
         }
         const double *bp = D + (32 + 8 * warp + fr) * RS + fk;
         const double *ap = D + (32 + fr) * RS + fk;
-#pragma unroll 2
-        for (int k0 = 0; k0 < 32; k0 += 4) {
-            const double bneg = -bp[k0];
+        double acc2[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};  // two chains: a dependent DMMA follows after 32-42 clk
 #pragma unroll
-            for (int mt = 0; mt < 4; mt++) dmma884(acc[mt], ap[mt * 8 * RS + k0], bneg);
+        for (int k0 = 0; k0 < 32; k0 += 8) {
+            const double bneg = -bp[k0], bneg2 = -bp[k0 + 4];
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) {
+                dmma884(acc[mt], ap[mt * 8 * RS + k0], bneg);
+                dmma884(acc2[mt], ap[mt * 8 * RS + k0 + 4], bneg2);
+            }
         }
         __syncwarp();
 #pragma unroll
         for (int mt = 0; mt < 4; mt++)
-            *reinterpret_cast<double2 *>(D + (32 + 8 * mt + fr) * RS + 32 + 8 * warp + 2 * fk) = make_double2(acc[mt][0], acc[mt][1]);
+            *reinterpret_cast<double2 *>(D + (32 + 8 * mt + fr) * RS + 32 + 8 * warp + 2 * fk) =
+                make_double2(acc[mt][0] + acc2[mt][0], acc[mt][1] + acc2[mt][1]);
     }
     __syncthreads();
     if (warp == 0) {
@@ -287,17 +319,19 @@ __device__ bool tile_potrf_mma(double *D, double *dinv, double *colbuf, double *
     return *sh_ok != 0;
 }
 
-// X <- X L^-T on the fp64 tensor cores.  X[64][RS] and L[64][RS] (lower, row-major) live in shared memory.
-// Column blocks of 8:  S_b = X_b - sum_{b'<b} X_b' L_{b,b'}^T  (DMMA),  X_b = S_b inv(L_bb)^T  (DMMA with the 8x8
-// inverses of the diagonal blocks, computed here by 64 threads).  Warp w owns rows 8w..8w+7 end to end, so the only
-// synchronisation inside is __syncwarp.  ~72 DMMA per warp instead of 2016 dependent DFMA per lane, and a rolled
-// loop instead of 50 KB of unrolled code (which ran mostly out of a cold instruction cache).
+// X <- X L^-T on the fp64 tensor cores.  X[8 NBLK][RS] and L[8 NBLK][RS] (lower, row-major) live in shared memory.
+// Right-looking over column blocks of 8:  X_b = S_b inv(L_bb)^T  (the 8x8 inverses of the diagonal blocks are computed
+// here by 8 NBLK threads), then every later block is updated at once, S_b' -= X_b L_{b',b}^T for b' > b.  What matters
+// is the number of DEPENDENT steps (a DMMA result is back after 32-42 clk, a fragment's round trip through shared
+// memory after ~85): per column block one DMMA for X_b (its two k-halves go to separate accumulators) and one for
+// the update of block b+1 (all other updates are independent of it) -- the left-looking form had b + 2 of them.  Warp w owns rows 8w..8w+7 end to end, so the only synchronisation
+// inside is __syncwarp.
 //   linv8: [8][96] scratch (8x8 inverse blocks, row stride 12);  tmp: [8 warps][160] scratch (8x8, row stride 20)
-__device__ __noinline__ void tile_trsm_mma(double *X, const double *L, const double *dinv, double *linv8, double *tmp,
-                                           int nblk = 8, int nrw = 8) {
-    // nblk: column blocks of 8 (size of L / 8);  nrw: row groups of 8 (rows of X / 8), one warp each
+template <int NBLK>
+__device__ __noinline__ void tile_trsm_mma_t(double *X, const double *L, const double *dinv, double *linv8, double *tmp) {
+    // NBLK: column blocks of 8 (size of L / 8) = row groups of 8 (rows of X / 8), one warp each
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 8 * nblk) {  // inverse of the 8x8 lower-triangular diagonal block b, column c
+    if (tid < 8 * NBLK) {  // inverse of the 8x8 lower-triangular diagonal block b, column c
         const int b = tid >> 3, c = tid & 7;
         double x[8];
 #pragma unroll
@@ -313,39 +347,53 @@ __device__ __noinline__ void tile_trsm_mma(double *X, const double *L, const dou
     }
     __syncthreads();
     const int fr = lane >> 2, fk = lane & 3;  // fragment row / k index
-    double *xrow = X + (8 * warp + fr) * RS;
-    double *tw = tmp + warp * 160;
-#pragma unroll 1
-    for (int b = 0; b < nblk && warp < nrw; b++) {
-        double acc0[2], acc1[2] = {0.0, 0.0};
-        {
+    if (warp < NBLK) {
+        double *xrow = X + (8 * warp + fr) * RS;
+        double *tw = tmp + warp * 160;
+        double c[NBLK][2], c2[NBLK][2];  // the two k-halves of every update accumulate separately
+#pragma unroll
+        for (int b = 0; b < NBLK; b++) {
             const double2 v = *reinterpret_cast<const double2 *>(xrow + 8 * b + 2 * fk);
-            acc0[0] = v.x, acc0[1] = v.y;
+            c[b][0] = v.x, c[b][1] = v.y;
+            c2[b][0] = c2[b][1] = 0.0;
         }
-        const double *lrow = L + (8 * b + fr) * RS + fk;
-#pragma unroll 1
-        for (int bp = 0; bp < b; bp++) {  // two independent accumulation chains
-            dmma884(acc0, xrow[8 * bp + fk], -lrow[8 * bp]);
-            dmma884(acc1, xrow[8 * bp + 4 + fk], -lrow[8 * bp + 4]);
+#pragma unroll
+        for (int b = 0; b < NBLK; b++) {
+            *reinterpret_cast<double2 *>(tw + fr * 20 + 2 * fk) = make_double2(c[b][0] + c2[b][0], c[b][1] + c2[b][1]);
+            __syncwarp();
+            double x0[2] = {0.0, 0.0}, x1[2] = {0.0, 0.0};
+            dmma884(x0, tw[fr * 20 + fk], linv8[b * 96 + fr * 12 + fk]);
+            dmma884(x1, tw[fr * 20 + 4 + fk], linv8[b * 96 + fr * 12 + 4 + fk]);
+            *reinterpret_cast<double2 *>(xrow + 8 * b + 2 * fk) = make_double2(x0[0] + x1[0], x0[1] + x1[1]);
+            __syncwarp();
+            if (b + 1 < NBLK) {
+                const double a0 = xrow[8 * b + fk], a1 = xrow[8 * b + 4 + fk];
+#pragma unroll
+                for (int bp = b + 1; bp < NBLK; bp++) {
+                    const double *lrow = L + (8 * bp + fr) * RS + 8 * b + fk;
+                    dmma884(c[bp], a0, -lrow[0]);
+                    dmma884(c2[bp], a1, -lrow[4]);
+                }
+            }
         }
-        *reinterpret_cast<double2 *>(tw + fr * 20 + 2 * fk) = make_double2(acc0[0] + acc1[0], acc0[1] + acc1[1]);
-        __syncwarp();
-        double x0[2] = {0.0, 0.0};
-        dmma884(x0, tw[fr * 20 + fk], linv8[b * 96 + fr * 12 + fk]);
-        dmma884(x0, tw[fr * 20 + 4 + fk], linv8[b * 96 + fr * 12 + 4 + fk]);
-        *reinterpret_cast<double2 *>(xrow + 8 * b + 2 * fk) = make_double2(x0[0], x0[1]);
-        __syncwarp();
     }
     __syncthreads();
 }
+__device__ __forceinline__ void tile_trsm_mma(double *X, const double *L, const double *dinv, double *linv8, double *tmp,
+                                              int nblk = 8, int nrw = 8) {
+    (void)nrw;
+    if (nblk == 4) tile_trsm_mma_t<4>(X, L, dinv, linv8, tmp);
+    else tile_trsm_mma_t<8>(X, L, dinv, linv8, tmp);
+}
 
 // fragment-distributed tile (acc) -> row-major shared tile S[64][RS]
-__device__ __forceinline__ void acc_to_smem_rs(const double (&acc)[8][2], double *S) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void acc_to_smem_rs(const double (&acc)[8][2], double *S, int cw) {
+    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int mt = 0; mt < 8; mt++)
-        *reinterpret_cast<double2 *>(S + (8 * mt + (lane >> 2)) * RS + 8 * warp + 2 * (lane & 3)) = make_double2(acc[mt][0], acc[mt][1]);
+        *reinterpret_cast<double2 *>(S + (8 * mt + (lane >> 2)) * RS + 8 * cw + 2 * (lane & 3)) = make_double2(acc[mt][0], acc[mt][1]);
 }
+__device__ __forceinline__ void acc_to_smem_rs(const double (&acc)[8][2], double *S) { acc_to_smem_rs(acc, S, threadIdx.x >> 5); }
 
 // MINB = 1: latency-bound sizes, the whole register file for the unrolled register kernels; MINB = 2: throughput-bound
 template <int MINB>
@@ -362,7 +410,6 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
     __shared__ int sh_tile, sh_ok, sh_ready;
     const int T = a.T, ld = a.ld, tid = threadIdx.x;
     const int total = T * (T + 1) / 2 + T;  // lower tiles + one rhs tile per column
-
     for (;;) {
         __syncthreads();
         if (tid == 0) {
@@ -437,11 +484,13 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
         const int i0 = i * TB;
         // ---- load A_ij into the accumulator fragments (damping on the diagonal of diagonal tiles: geom_kernels.cu:1176)
         double acc[8][2];
+        const int cw = (i == j) ? diag_col(tid >> 5) : (tid >> 5);  // this warp's column block (see tile_gemm_sub)
+        const int mt0 = (i == j) ? cw : 0;                          // diagonal tiles: lower blocks only
         {
-            const int lane = tid & 31, warp = tid >> 5;
+            const int lane = tid & 31;
 #pragma unroll
             for (int mt = 0; mt < 8; mt++) {
-                const int r = 8 * mt + (lane >> 2), c = 8 * warp + 2 * (lane & 3);
+                const int r = 8 * mt + (lane >> 2), c = 8 * cw + 2 * (lane & 3);
                 if (a.Ain) {
                     const double *src = a.Ain + (size_t)(i0 + r) * ld + j0 + c;
                     acc[mt][0] = mc_load_sum(src);
@@ -497,19 +546,25 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
                 issue(0);
                 cp_async_commit();
             }
-            for (int k = 0; k < kend; k++) {
-                if (k + 1 < kend) {
-                    ensure(k + 1);
-                    issue(k + 1);  // its buffers were last read by step k-1, which ended with a barrier
+            // two copies of the loop (off-diagonal / diagonal tile) so that the hot off-diagonal one stays a tight body
+            auto kloop = [&](auto is_diag) {
+                for (int k = 0; k < kend; k++) {
+                    if (k + 1 < kend) {
+                        ensure(k + 1);
+                        issue(k + 1);  // its buffers were last read by step k-1, which ended with a barrier
+                    }
+                    cp_async_commit();
+                    cp_async_wait<1>();
+                    __syncthreads();
+                    if (k == kend - 1) TRACE(t, 7);
+                    const double *Ak = (k & 1) ? As2 : As, *Bk = (k & 1) ? Bs2 : Bs;
+                    if constexpr (decltype(is_diag)::value) tile_gemm_sub(acc, Ak, Ak, cw, mt0);
+                    else tile_gemm_sub(acc, Ak, Bk);
+                    __syncthreads();
                 }
-                cp_async_commit();
-                cp_async_wait<1>();
-                __syncthreads();
-                if (k == kend - 1) TRACE(t, 7);
-                const double *Ak = (k & 1) ? As2 : As, *Bk = (k & 1) ? Bs2 : Bs;
-                tile_gemm_sub(acc, Ak, (i != j) ? Bk : Ak);
-                __syncthreads();
-            }
+            };
+            if (i == j) kloop(std::true_type{});
+            else kloop(std::false_type{});
             cp_async_wait<0>();
             kstart = kend > 0 ? kend : 0;
         }
@@ -527,7 +582,7 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
                 if (tid < TB) dinv[tid] = __ldcg(a.dinv + kk0 + tid);
                 __syncthreads();
                 tile_trsm_mma(As, Bs, dinv, linv8, tmpw);
-                tile_gemm_sub(acc, As, As);
+                tile_gemm_sub(acc, As, As, cw, mt0);
                 __syncthreads();
                 continue;
             }
@@ -537,10 +592,11 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
             load_tile_R(As, a.H + (size_t)i0 * ld + k * TB, ld);
             if (i != j) load_tile_R(Bs, a.H + (size_t)j0 * ld + k * TB, ld);
             __syncthreads();
-            tile_gemm_sub(acc, As, (i != j) ? Bs : As);
+            if (i != j) tile_gemm_sub(acc, As, Bs);
+            else tile_gemm_sub(acc, As, As, cw, mt0);
             __syncthreads();
         }
-        acc_to_smem_rs(acc, As);
+        acc_to_smem_rs(acc, As, cw);
         __syncthreads();
         TRACE(t, 2);
         if (i == j) {
@@ -548,9 +604,10 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
             TRACE(t, 4);
             if (!ok && tid == 0) *a.fail = 1;
             // store L_jj (zero above the diagonal) and 1/diag
-            for (int idx = tid; idx < TB * TB; idx += CT) {
-                const int r = idx >> 6, c = idx & 63;
-                a.H[(size_t)(i0 + r) * ld + j0 + c] = (c <= r) ? As[r * RS + c] : 0.0;
+            for (int idx = tid; idx < TB * TB / 2; idx += CT) {
+                const int r = idx >> 5, c = (idx & 31) * 2;
+                const double2 v = *reinterpret_cast<const double2 *>(As + r * RS + c);
+                *reinterpret_cast<double2 *>(a.H + (size_t)(i0 + r) * ld + j0 + c) = make_double2(c <= r ? v.x : 0.0, c + 1 <= r ? v.y : 0.0);
             }
             if (tid < TB) a.dinv[j0 + tid] = dinv[tid];
             TRACE(t, 5);

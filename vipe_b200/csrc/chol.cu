@@ -86,7 +86,8 @@ struct CholArgs {
     int ld, T, n;
     float lm, ep;
     int *flags;    // [(T+1) x T] tile ready flags, value == epoch when ready; row T is the rhs row
-    int *xflags;   // [T] ready flags of the backward substitution
+    unsigned long long *xs;  // [npad] x of the backward substitution as self-validating words (0 = not there yet)
+    unsigned long long *ldiag;  // [T][64*64 + 64] factorised diagonal tiles + 1/diag as self-validating words (fast path)
     int *preflags; // [T] tile (j+1, j) is available BEFORE its solve against L_jj, parked in the unused upper tile (j, j+1)
     int *counter;  // [2] tile counters (factorisation, backward), zero on entry
     int *fail;     // zero on entry
@@ -156,6 +157,65 @@ __device__ __forceinline__ void tile_gemm_sub(double (&acc)[8][2], const double 
 __device__ __forceinline__ void tile_gemm_sub(double (&acc)[8][2], const double *As, const double *Bs) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     tile_gemm_sub_from<0>(acc, As + (lane >> 2) * RS + (lane & 3), Bs + (8 * warp + (lane >> 2)) * RS + (lane & 3));
+}
+
+// ---- self-validating exchange of the factorised diagonal tiles ------------------------------------------------
+// The hop "diagonal tile factorised -> its consumers start" is on the critical path twice per column.  Through a
+// ready flag it costs a barrier, a release fence and the flag store on the writer's side, then a flag poll and only
+// then the tile load on the reader's side.  Here the tile itself is the message: the buffer is zeroed before the
+// solve, the writer stores every 8-byte word with a non-zero bit pattern (+0.0 travels as -0.0), and every reader
+// thread polls exactly the words it needs until all of them are non-zero -- no fence, no flag, one trip to L2 after
+// the data lands.  (H and the regular flag are still written afterwards for the readers that are not in a hurry.)
+constexpr int kFastTile = TB * TB + TB;  // words per diagonal tile: L (row-major 64x64, zero above the diagonal) + 1/diag
+__device__ __forceinline__ unsigned long long nz_bits(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return b == 0ull ? 0x8000000000000000ull : b;
+}
+// The tile travels in two halves: columns 0..31 (L11, L21, 1/diag[0:32]) are final before the second 32x32 block is
+// factorised, so the otherwise idle warps 1..7 send them while warp 0 walks the second half of the pivot chain, and
+// the readers run the first four column blocks of their tile solve under it.  Half B = L22 and 1/diag[32:64]; the
+// upper right block is never read.
+//   `t` / `nt`: index and number of the calling threads (half A is stored by 224 threads, half B by all 256)
+__device__ __forceinline__ void fast_half_store(unsigned long long *ft, const double *S, const double *dinv, int half, int t, int nt) {
+    const int row0 = half ? 32 : 0, col0 = half ? 32 : 0, nrows = half ? 32 : 64;
+    for (int idx = t; idx < nrows * 16; idx += nt) {
+        const int r = row0 + (idx >> 4), c = col0 + (idx & 15) * 2;
+        const double2 v = *reinterpret_cast<const double2 *>(S + r * RS + c);
+        const unsigned long long b0 = nz_bits(c <= r ? v.x : 0.0), b1 = nz_bits(c + 1 <= r ? v.y : 0.0);
+        asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(ft + r * TB + c), "l"(b0), "l"(b1) : "memory");
+    }
+    if (t < 32)
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(ft + TB * TB + col0 + t), "l"(nz_bits(dinv[col0 + t])) : "memory");
+}
+// all threads call; returns with the half in S (row stride RS) and its 1/diag in dinv (caller adds the barrier)
+template <int HALF>
+__device__ __forceinline__ void fast_half_load(double *S, double *dinv, const unsigned long long *ft) {
+    constexpr int row0 = HALF ? 32 : 0, col0 = HALF ? 32 : 0, nrows = HALF ? 32 : 64;
+    constexpr int U = nrows * 16 / CT;
+    unsigned long long lo[U], hi[U], dv = 1ull;
+    for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int idx = threadIdx.x + u * CT;
+            const int r = row0 + (idx >> 4), c = col0 + (idx & 15) * 2;
+            asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo[u]), "=l"(hi[u]) : "l"(ft + r * TB + c) : "memory");
+        }
+        if (threadIdx.x < 32)
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(dv) : "l"(ft + TB * TB + col0 + threadIdx.x) : "memory");
+#pragma unroll
+        for (int u = 0; u < U; u++) ok = ok && lo[u] != 0ull && hi[u] != 0ull;
+        ok = ok && dv != 0ull;
+        if (ok) break;
+        __nanosleep(20);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int idx = threadIdx.x + u * CT;
+        const int r = row0 + (idx >> 4), c = col0 + (idx & 15) * 2;
+        *reinterpret_cast<double2 *>(S + r * RS + c) = make_double2(__longlong_as_double((long long)lo[u]), __longlong_as_double((long long)hi[u]));
+    }
+    if (threadIdx.x < 32) dinv[col0 + threadIdx.x] = __longlong_as_double((long long)dv);
 }
 
 // load a 64x64 tile (global row-major, leading dim ld) into shared memory row-major with stride RS
@@ -276,7 +336,13 @@ __device__ __noinline__ void tile_trsm_mma_t(double *X, const double *L, const d
 
 // Tensor-core version of tile_potrf for tiles stored with row stride RS: potrf32 (warp 0, registers) ->
 // L21 = A21 L11^-T (DMMA) -> A22 -= L21 L21^T (DMMA) -> potrf32.  All threads must call.
-__device__ bool tile_potrf_mma(double *D, double *dinv, double *colbuf, double *linv8, double *tmp, int *sh_ok) {
+struct NoMid {
+    __device__ __forceinline__ void operator()(int) const {}
+};
+// `mid(t)`, t = 0..223, runs on warps 1..7 while warp 0 factorises the second 32x32 block (columns 0..31 of L are final
+// by then): the dataflow solver sends the first half of the tile to its readers there.
+template <class Mid = NoMid>
+__device__ bool tile_potrf_mma(double *D, double *dinv, double *colbuf, double *linv8, double *tmp, int *sh_ok, Mid mid = Mid()) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (warp == 0) {
         const bool ok = warp_potrf32_smem(D, dinv, colbuf);
@@ -314,6 +380,8 @@ __device__ bool tile_potrf_mma(double *D, double *dinv, double *colbuf, double *
     if (warp == 0) {
         const bool ok = warp_potrf32_smem(D + 32 * RS + 32, dinv + 32, colbuf);
         if (!ok && lane == 0) *sh_ok = 0;
+    } else {
+        mid(tid - 32);
     }
     __syncthreads();
     return *sh_ok != 0;
@@ -384,6 +452,65 @@ __device__ __forceinline__ void tile_trsm_mma(double *X, const double *L, const 
     (void)nrw;
     if (nblk == 4) tile_trsm_mma_t<4>(X, L, dinv, linv8, tmp);
     else tile_trsm_mma_t<8>(X, L, dinv, linv8, tmp);
+}
+
+// X <- X L_jj^-T with L_jj taken from its fast copy `ft` as the two halves arrive (see fast_half_store): same right-looking
+// solve as tile_trsm_mma_t<8>, column blocks 0..3 after half A, 4..7 after half B.  L (shared, row stride RS), dinv:
+// staging for the tile.  All threads must call; ends with a block barrier.
+__device__ __noinline__ void tile_trsm_fast(double *X, double *L, double *dinv, double *linv8, double *tmp, const unsigned long long *ft) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    double *xrow = X + (8 * warp + fr) * RS;
+    double *tw = tmp + warp * 160;
+    double c[8][2], c2[8][2];
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const double2 v = *reinterpret_cast<const double2 *>(xrow + 8 * b + 2 * fk);
+        c[b][0] = v.x, c[b][1] = v.y;
+        c2[b][0] = c2[b][1] = 0.0;
+    }
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        if (half == 0) fast_half_load<0>(L, dinv, ft);
+        else fast_half_load<1>(L, dinv, ft);
+        __syncthreads();
+        if (tid < 32) {  // inverses of this half's four 8x8 diagonal blocks, one column per thread
+            const int b = 4 * half + (tid >> 3), cc = tid & 7;
+            double x[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                double sacc = (r == cc) ? 1.0 : 0.0;
+#pragma unroll
+                for (int p = 0; p < 8; p++)
+                    if (p < r && p >= cc) sacc = fma(-L[(8 * b + r) * RS + 8 * b + p], x[p], sacc);
+                x[r] = (r >= cc) ? sacc * dinv[8 * b + r] : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++) linv8[b * 96 + r * 12 + cc] = x[r];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int bb = 0; bb < 4; bb++) {
+            const int b = 4 * half + bb;
+            *reinterpret_cast<double2 *>(tw + fr * 20 + 2 * fk) = make_double2(c[b][0] + c2[b][0], c[b][1] + c2[b][1]);
+            __syncwarp();
+            double x0[2] = {0.0, 0.0}, x1[2] = {0.0, 0.0};
+            dmma884(x0, tw[fr * 20 + fk], linv8[b * 96 + fr * 12 + fk]);
+            dmma884(x1, tw[fr * 20 + 4 + fk], linv8[b * 96 + fr * 12 + 4 + fk]);
+            *reinterpret_cast<double2 *>(xrow + 8 * b + 2 * fk) = make_double2(x0[0] + x1[0], x0[1] + x1[1]);
+            __syncwarp();
+            if (b + 1 < 8) {
+                const double a0 = xrow[8 * b + fk], a1 = xrow[8 * b + 4 + fk];
+#pragma unroll
+                for (int bp = b + 1; bp < 8; bp++) {
+                    const double *lrow = L + (8 * bp + fr) * RS + 8 * b + fk;
+                    dmma884(c[bp], a0, -lrow[0]);
+                    dmma884(c2[bp], a1, -lrow[4]);
+                }
+            }
+        }
+    }
+    __syncthreads();
 }
 
 // fragment-distributed tile (acc) -> row-major shared tile S[64][RS]
@@ -576,12 +703,9 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
                 const int kk0 = k * TB;
                 wait_flag(a.preflags + k, a.epoch);
                 load_tile_R(As, a.H + (size_t)kk0 * ld + j0, ld);  // pre-solve copy of tile (j, j-1), parked at (j-1, j)
-                wait_flag(a.flags + (size_t)k * T + k, a.epoch);
-                TRACE(t, 7);
-                load_tile_R(Bs, a.H + (size_t)kk0 * ld + kk0, ld);  // L_kk, row-major
-                if (tid < TB) dinv[tid] = __ldcg(a.dinv + kk0 + tid);
                 __syncthreads();
-                tile_trsm_mma(As, Bs, dinv, linv8, tmpw);
+                TRACE(t, 7);
+                tile_trsm_fast(As, Bs, dinv, linv8, tmpw, a.ldiag + (size_t)k * kFastTile);  // L_kk as its halves arrive
                 tile_gemm_sub(acc, As, As, cw, mt0);
                 __syncthreads();
                 continue;
@@ -600,7 +724,9 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
         __syncthreads();
         TRACE(t, 2);
         if (i == j) {
-            const bool ok = tile_potrf_mma(As, dinv, col, linv8, tmpw, &sh_ok);
+            unsigned long long *ft = a.ldiag + (size_t)j * kFastTile;  // the latency-critical readers take this copy
+            const bool ok = tile_potrf_mma(As, dinv, col, linv8, tmpw, &sh_ok, [&](int t2) { if (t2 < 64) fast_half_store(ft, As, dinv, 0, t2, 64); });  // two warps: more of them slow the pivot chain
+            fast_half_store(ft, As, dinv, 1, tid, CT);
             TRACE(t, 4);
             if (!ok && tid == 0) *a.fail = 1;
             // store L_jj (zero above the diagonal) and 1/diag
@@ -635,12 +761,8 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
                 }
                 publish_flag(a.preflags + j, a.epoch);
             }
-            wait_flag(a.flags + (size_t)j * T + j, a.epoch);
-            load_tile_R(Bs, a.H + (size_t)j0 * ld + j0, ld);  // L_jj, row-major
-            if (tid < TB) dinv[tid] = __ldcg(a.dinv + j0 + tid);
-            __syncthreads();
             TRACE(t, 3);
-            tile_trsm_mma(As, Bs, dinv, linv8, tmpw);
+            tile_trsm_fast(As, Bs, dinv, linv8, tmpw, a.ldiag + (size_t)j * kFastTile);  // L_jj as its halves arrive
             TRACE(t, 4);
             for (int idx = tid; idx < TB * TB; idx += CT) {
                 const int r = idx >> 6, c = idx & 63;
@@ -678,6 +800,7 @@ __global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
             Ld[r * (TB + 1) + k2] = v.x;
             Ld[r * (TB + 1) + k2 + 1] = v.y;
         }
+        const double yj = (tid < TB) ? __ldcg(a.b + j0 + tid) : 0.0;  // y_j (from the factor kernel), fetched off the x chain
         double s = 0.0;
         for (int i = T - 1; i > j; i--) {
             // stage L_ij while x_i may still be in flight
@@ -695,8 +818,15 @@ __global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
                 Ls[r * (TB + 1) + k2] = v[u].x;
                 Ls[r * (TB + 1) + k2 + 1] = v[u].y;
             }
-            wait_flag(a.xflags + i, a.epoch);
-            if (tid < TB) xi[tid] = __ldcg(a.b + i * TB + tid);
+            // x_i arrives as self-validating 8-byte words (zero bits = not written yet; a true +0.0 travels as -0.0): every
+            // thread polls its own entry, one trip to L2 after the data lands instead of fence + flag + flag poll + load
+            if (tid < TB) {
+                unsigned long long v;
+                do {
+                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.xs + i * TB + tid) : "memory");
+                } while (v == 0ull);
+                xi[tid] = __longlong_as_double((long long)v);
+            }
             __syncthreads();
 #pragma unroll
             for (int p = 0; p < 16; p++) s = fma(Ls[(q * 16 + p) * (TB + 1) + c], xi[q * 16 + p], s);
@@ -704,7 +834,7 @@ __global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
         }
         part[q * TB + c] = s;
         __syncthreads();
-        if (tid < TB) xi[tid] = __ldcg(a.b + j0 + tid) - (part[tid] + part[TB + tid] + part[2 * TB + tid] + part[3 * TB + tid]);
+        if (tid < TB) xi[tid] = yj - (part[tid] + part[TB + tid] + part[2 * TB + tid] + part[3 * TB + tid]);
         __syncthreads();
         {   // x_j = L_jj^-T v : thread (c, q) sums a quarter of row c, quarters combined through shared memory
             double acc = 0.0;
@@ -715,10 +845,12 @@ __global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
         __syncthreads();
         if (tid < TB) {
             const double x = part[tid] + part[TB + tid] + part[2 * TB + tid] + part[3 * TB + tid];
+            unsigned long long bits = (unsigned long long)__double_as_longlong(x);
+            if (bits == 0ull) bits = 0x8000000000000000ull;
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(a.xs + j0 + tid), "l"(bits) : "memory");
             a.b[j0 + tid] = x;
             if (j0 + tid < a.n) a.dx[j0 + tid] = failed ? 0.0f : (float)x;
         }
-        publish_flag(a.xflags + j, a.epoch);
     }
 }
 
@@ -893,7 +1025,9 @@ cudaError_t launch_small_solve_batch(double *sys, const long long *prob_hoff, co
 cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx, int *scratch,
                                 double *dinv, double *linvT, const double *dampdiag, const double *Ain, int epoch,
                                 cudaStream_t st, int *launches) {
-    // scratch (ints): [0..1] counters, [2] fail, [16 .. 16+T) xflags, [16+T .. 16+2T) preflags, then (T+1)*T tile flags
+    // scratch (ints): [0..1] counters, [2] fail, [16 .. 16+T) unused, [16+T .. 16+2T) preflags, (T+1)*T tile flags, then
+    // (16-byte aligned) npad 64-bit words for the backward substitution's x exchange and T * (64*64 + 64) words for the
+    // diagonal tiles' fast copies; all zeroed by the memset below
     const int T = npad / TB;
     (void)epoch;
     if (T <= 2) {
@@ -914,9 +1048,10 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     a.ep = ep;
     a.counter = scratch;
     a.fail = scratch + 2;
-    a.xflags = scratch + 16;
     a.preflags = scratch + 16 + T;
     a.flags = scratch + 16 + 2 * T;
+    a.xs = reinterpret_cast<unsigned long long *>(scratch + ((16 + 2 * (size_t)T + (size_t)(T + 1) * T + 3) & ~(size_t)3));  // 16-byte aligned
+    a.ldiag = a.xs + npad;
     a.epoch = 1;
     a.dx = dx;
     a.dinv = dinv;
@@ -950,7 +1085,7 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
 
 size_t chol_scratch_ints(int npad) {
     const int T = npad / TB;
-    return 16 + 2 * (size_t)T + (size_t)(T + 1) * T;
+    return ((16 + 2 * (size_t)T + (size_t)(T + 1) * T + 3) & ~(size_t)3) + 2 * (size_t)npad + 2 * (size_t)T * (TB * TB + TB);
 }
 
 }  // namespace vba

@@ -337,3 +337,30 @@ def test_identity_plan_cache_sees_in_place_edits(slam_ext, dev):
     p2 = slam_ext.ba_plan(a[7], a[8], 8, 48, 64, 1, 8)
     assert p2 is not p1
     assert slam_ext.ba_plan(a[7].clone(), a[8].clone(), 8, 48, 64, 1, 8) is p2  # same content, other objects: hash cache
+
+
+def test_host_feed_matches_direct_calls(slam_ext, dev):
+    """HostFeed (uploads on a copy stream, two alternating device argument sets) gives the results of calling
+    slam_ext.ba on device copies, call after call, including slot reuse (not bit-for-bit: the assembly of the reduced
+    system uses fp64 atomics, whose order varies from run to run)."""
+    from vipe_b200.host_feed import HostFeed
+
+    problems_ = [make_problem("c1"), make_problem("c2"), make_problem("c1"), make_problem("c2"), make_problem("c1")]
+    want = []
+    for pr in problems_:
+        a = pr.args(dev)
+        slam_ext.ba(*a)
+        want.append((a[0].cpu(), a[1].cpu()))
+    feed = HostFeed(dev)
+    host = [[x.pin_memory() if torch.is_tensor(x) else x for x in pr.args()] for pr in problems_]
+    outs = [(torch.empty_like(h[0]).pin_memory(), torch.empty_like(h[1]).pin_memory()) for h in host]
+    feed.prefetch(host[0])
+    for q in range(len(host)):
+        if q + 1 < len(host):
+            feed.prefetch(host[q + 1])
+        feed.run(out_poses=outs[q][0], out_disps=outs[q][1])
+    torch.cuda.synchronize()
+    for (p, d), (wp, wd) in zip(outs, want):
+        assert torch.allclose(p, wp, rtol=1e-5, atol=1e-6) and torch.allclose(d, wd, rtol=1e-5, atol=1e-6)
+    with pytest.raises(RuntimeError):
+        feed.run()  # nothing prefetched

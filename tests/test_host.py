@@ -130,3 +130,13 @@ def test_synthetic_configs_match_baseline(problems):
 
     again = make_problem("c1")
     assert torch.equal(again.targets, pr1.targets) and torch.equal(again.poses, pr1.poses)
+
+
+def test_host_feed_needs_cuda():
+    """The host-memory feeder is CUDA-only like the operator itself (no CPU fallback)."""
+    import pytest
+
+    from vipe_b200.host_feed import HostFeed
+
+    with pytest.raises(RuntimeError):
+        HostFeed("cpu")

@@ -86,6 +86,47 @@ __global__ void __launch_bounds__(CT) micro_kernel(double *out, long long *clk) 
         }
         TIME_VARIANT(0) TIME_VARIANT(1) TIME_VARIANT(2) TIME_VARIANT(3) TIME_VARIANT(4)
         out[lane] = a[lane & 31] + inv;
+        // rolled loops (fit the instruction cache): (5) the pivot dependency chain alone, (6) the whole factorisation with
+        // the block in shared memory, column-major Am[k][lane]: LDS + DFMA + STS per trailing entry
+        {
+            double diag = 100.0 + lane, a0 = 1.0 / (1 + lane);
+            long long q0 = clock64();
+#pragma unroll 1
+            for (int j = 0; j < 32; j++) {
+                const double piv = __shfl_sync(0xffffffffu, diag, j);
+                const double iv = fast_rsqrt(piv);
+                const double l = ((lane == j) ? piv : a0) * iv;
+                diag = fma(-l, l, diag);
+                a0 = fma(l, 1e-3, a0);
+            }
+            long long q1 = clock64();
+            if (lane == 0) clk[21] = q1 - q0;
+            out[lane] += diag + a0;
+        }
+        {
+            double *Am = Bs;  // [32][33] column-major scratch
+            for (int c = 0; c < 32; c++) Am[c * 33 + lane] = (lane == c) ? 100.0 + c : 1.0 / (1 + abs(lane - c));
+            __syncwarp();
+            double diag = Am[lane * 33 + lane];
+            long long q0 = clock64();
+#pragma unroll 1
+            for (int j = 0; j < 32; j++) {
+                const double piv = __shfl_sync(0xffffffffu, diag, j);
+                const double iv = fast_rsqrt(piv);
+                double l = ((lane == j) ? piv : Am[j * 33 + lane]) * iv;
+                if (lane < j) l = 0.0;
+                Am[j * 33 + lane] = l;
+                diag = fma(-l, l, diag);
+                col[lane] = l;
+                __syncwarp();
+#pragma unroll 4
+                for (int k = j + 1; k < 32; k++) Am[k * 33 + lane] = fma(-l, col[k], Am[k * 33 + lane]);
+                __syncwarp();
+            }
+            long long q1 = clock64();
+            if (lane == 0) clk[22] = q1 - q0;
+            out[lane] += Am[lane * 33 + (lane & 7)];
+        }
     }
     __syncthreads();
     long long t2 = clock64();
@@ -119,6 +160,7 @@ int main(int argc, char **argv) {
             cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
             printf("warp_potrf32 repeated in a loop: %lld %lld %lld %lld\n", h[8], h[9], h[10], h[11]);
             printf("variants (warm): full %lld | rsqrt seed only %lld | no rsqrt %lld | no pivot shuffle %lld | no column exchange %lld\n", h[16], h[17], h[18], h[19], h[20]);
+            printf("rolled loops: pivot chain alone %lld | whole potrf32 with the block in shared memory %lld\n", h[21], h[22]);
             printf("cycles: tile_potrf_mma (64x64) %lld | tile_trsm_mma %lld | tile_gemm_sub %lld   (%s)\n", h[0], h[1], h[2], cudaGetErrorString(cudaGetLastError()));
         }
         return 0;

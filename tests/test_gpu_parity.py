@@ -190,6 +190,24 @@ def test_failed_factorisation_is_silent_zero_update(slam_ext, dev):
     assert torch.equal(a[0].cpu(), pr.poses)
 
 
+@pytest.mark.timeout(120)
+def test_failed_factorisation_tiled_solver(slam_ext, dev):
+    """Same on the tile-dataflow solver (6P > 128): a NaN weight poisons the system; the factorisation must finish (its
+    tiles and the backward substitution's x travel as self-validating words -- NaN is a valid word, nothing may spin on
+    it), report failure and leave the poses alone; the next call on clean inputs works."""
+    cfg = BAConfig("tiled_fail", 41, 48, 300, 24, 32, 2, 1e-4, 0.1)
+    pr = make_problem(cfg)
+    a = pr.args(dev)
+    a[5][3, 0, 0, 0] = float("nan")
+    a[14] = True
+    dx, _ = slam_ext.ba(*a)
+    torch.cuda.synchronize()
+    assert torch.equal(dx.cpu(), torch.zeros(pr.t1 - pr.t0, 6))
+    assert torch.equal(a[0].cpu(), pr.poses)
+    r = _compare(slam_ext, dev, pr)
+    assert r["te"] <= TOL_T and r["re"] <= TOL_R and r["de"] <= TOL_D, (r["te"], r["re"], r["de"])
+
+
 @pytest.mark.parametrize("name", ["c3", "c4"])
 def test_full_size_properties(slam_ext, dev, name):
     """Size-independent properties at BASELINE.json's full sizes (the oracle is too slow at C4):

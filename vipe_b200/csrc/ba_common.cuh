@@ -105,7 +105,8 @@ struct ReduceArgs {
     const float *fpart = nullptr, *ffpart = nullptr;  // focal pass partials (null: focal length fixed)
     int ntile_f = 0, focal_row = 0;
     float focal_lm = 0.0f;
-    double *msc;   // M scratch
+    double *msc;   // M scratch (used when a frame's blocks do not fit shared memory)
+    int msc_smem = 0;  // 1: M lives in the kernel's shared memory (set by launch_frame_reduce)
     double *hsys;  // per problem: [n*n] row-major lower triangle (+ full diagonal blocks), then b [n], then diag(A) [n]
                    //   (diag(A): the pose Hessian alone, before the Schur complement, for damp_on_pose_hessian)
     int motion_only;

@@ -333,6 +333,21 @@ __device__ __forceinline__ void add_block_entry(double *H, int n, int pa, int r,
     }
 }
 
+// sum of `n` fp32 partial records spaced `stride` apart, in tile order, in fp64.  The loads of a chunk of 8 are issued
+// before the first add: a rolled `s += p[t * stride]` loop serialises them (the add waits for its load and, issue being
+// in order, holds back the next load), which made this latency-bound kernel pay one trip to L2 per tile.
+__device__ __forceinline__ double tile_sum(const float *p, size_t stride, int n) {
+    double s = 0.0;
+    for (int t0 = 0; t0 < n; t0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = (t0 + u < n) ? __ldg(p + (size_t)(t0 + u) * stride) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; u++) s += (double)v[u];
+    }
+    return s;
+}
+
 __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
     extern __shared__ __align__(16) double dsm[];
     const Tables &tb = a.tb;
@@ -369,23 +384,20 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
     for (int idx = tid; idx < d * kEdgeVals; idx += NT) {
         const int m = idx / kEdgeVals, r = idx - m * kEdgeVals;
         const float *ep = a.epart + ((size_t)(s0 + m) * ntile) * kEdgeStride + r;
-        double s = 0.0;
-        for (int t = 0; t < ntile; t++) s += (double)ep[(size_t)t * kEdgeStride];
-        hs[idx] = s;
+        hs[idx] = tile_sum(ep, kEdgeStride, ntile);
     }
     __syncthreads();
 
     const int npairs = d * (d + 1) / 2;
     const int rec = npairs * 36 + 6 * d;
-    double *msc = a.msc + tb.mbase[k];
+    // M(m, m') blocks: written below, read back by every thread for T = sum_m G_m M; shared memory when they fit
+    double *msc = a.msc_smem ? reinterpret_cast<double *>(aj + ((d + 1) & ~1)) : a.msc + tb.mbase[k];
     const float *gp = a.gpart + tb.gbase[k];
 
     // g_m = v_j,m - sum_tiles sb_m
     for (int idx = tid; idx < d * 6; idx += NT) {
         const int m = idx / 6, r = idx - m * 6;
-        double s = 0.0;
-        if (!a.motion_only)
-            for (int t = 0; t < ntile; t++) s += (double)gp[(size_t)t * rec + npairs * 36 + idx];
+        const double s = a.motion_only ? 0.0 : tile_sum(gp + npairs * 36 + idx, rec, ntile);
         const double g = hs[m * kEdgeVals + 20 + r] - s;
         gv[idx] = g;
         if (aj[m] >= 0) atomicAdd(bsys + 6 * aj[m] + r, g);
@@ -396,9 +408,7 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
         const int r = rc / 6, c = rc - r * 6;
         int m, mp;
         decode_pair(p, m, mp);
-        double y = 0.0;
-        if (!a.motion_only)
-            for (int t = 0; t < ntile; t++) y += (double)gp[(size_t)t * rec + idx];
+        const double y = a.motion_only ? 0.0 : tile_sum(gp + idx, rec, ntile);
         double v = -y;
         if (m == mp) {
             const int hi = r >= c ? r : c, lo = r >= c ? c : r;
@@ -863,10 +873,14 @@ cudaError_t launch_linearize(const LinArgs &a, int nframes, int dmax, bool motio
 
 cudaError_t launch_frame_reduce(const ReduceArgs &a, int nframes, int dmax, cudaStream_t st) {
     if (nframes <= 0) return cudaSuccess;
-    const size_t sm = (size_t)dmax * (36 + 36 + 27 + 6 + (a.fpart ? 20 : 0)) * sizeof(double) + (size_t)dmax * sizeof(int) + 16;
+    size_t sm = (size_t)dmax * (36 + 36 + 27 + 6 + (a.fpart ? 20 : 0)) * sizeof(double) + (size_t)(dmax + 2) * sizeof(int) + 16;
+    const size_t msc_bytes = (size_t)dmax * (dmax + 1) / 2 * 36 * sizeof(double);
+    ReduceArgs b = a;
+    b.msc_smem = (sm + msc_bytes <= 96 * 1024) ? 1 : 0;  // backend degrees (~10-20 edges per frame) fit; hubs fall back to global
+    if (b.msc_smem) sm += msc_bytes;
     cudaError_t err = cudaFuncSetAttribute(frame_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (err != cudaSuccess) return err;
-    frame_reduce_kernel<<<nframes, 256, sm, st>>>(a);
+    frame_reduce_kernel<<<nframes, 256, sm, st>>>(b);
     return cudaGetLastError();
 }
 

@@ -112,6 +112,12 @@ __global__ void __launch_bounds__(2 * NT, (MOTION && NT == 256) ? 2 : 1) lineari
     // the first edge's loads leave before the barrier (edge id straight from the table, not from the staged constants):
     // their trip to HBM overlaps the pose prologue of the d threads above
     if (inb && half < d) issue_loads_e(tb.fedge[s0 + half]);
+    // sensor disparity and damping of this pixel pair (used after the edge loop by the even-edge half): fetched now
+    float2 ds_pre = make_float2(0.0f, 0.0f), et_pre = make_float2(0.0f, 0.0f);
+    if (!MOTION && inb && half == 0) {
+        ds_pre = __ldg(reinterpret_cast<const float2 *>(a.dsens + (size_t)src * HW + px0));
+        et_pre = __ldg(reinterpret_cast<const float2 *>(a.eta + (size_t)k * HW + px0));
+    }
     __syncthreads();
 
     for (int m = half; m < d; m += 2) {
@@ -223,8 +229,7 @@ __global__ void __launch_bounds__(2 * NT, (MOTION && NT == 256) ? 2 : 1) lineari
             // disparity block: damping / sensor prior (:1359-1370), eliminate: Q = 1/C
             float2 qv = make_float2(0.0f, 0.0f), wz = make_float2(0.0f, 0.0f);
             if (inb) {
-                const float2 ds = __ldg(reinterpret_cast<const float2 *>(a.dsens + (size_t)src * HW + px0));
-                const float2 et = __ldg(reinterpret_cast<const float2 *>(a.eta + (size_t)k * HW + px0));
+                const float2 ds = ds_pre, et = et_pre;
                 const int fflags = a.opt.frame_flags ? a.opt.frame_flags[k] : 0;
                 disparity_block(Cacc.x, Wacc.x, h.x, ds.x, et.x, fflags, a.opt, qv.x, wz.x);
                 disparity_block(Cacc.y, Wacc.y, h.y, ds.y, et.y, fflags, a.opt, qv.y, wz.y);

@@ -794,11 +794,20 @@ __global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
         if (j < 0) return;
         const int j0 = j * TB;
         const int c = tid & 63, q = tid >> 6;
-        for (int idx = tid; idx < TB * TB / 2; idx += CT) {  // Ld <- L_jj^-T (upper triangular)
-            const int r = idx >> 5, k2 = (idx & 31) * 2;
-            const double2 v = __ldcg(reinterpret_cast<const double2 *>(a.linvT + (size_t)j * TB * TB + r * TB + k2));
-            Ld[r * (TB + 1) + k2] = v.x;
-            Ld[r * (TB + 1) + k2 + 1] = v.y;
+        {   // Ld <- L_jj^-T (upper triangular); all loads in flight before the first store
+            double2 v[TB * TB / 2 / CT];
+#pragma unroll
+            for (int u = 0; u < TB * TB / 2 / CT; u++) {
+                const int idx = tid + u * CT;
+                v[u] = __ldcg(reinterpret_cast<const double2 *>(a.linvT + (size_t)j * TB * TB + (idx >> 5) * TB + (idx & 31) * 2));
+            }
+#pragma unroll
+            for (int u = 0; u < TB * TB / 2 / CT; u++) {
+                const int idx = tid + u * CT;
+                const int r = idx >> 5, k2 = (idx & 31) * 2;
+                Ld[r * (TB + 1) + k2] = v[u].x;
+                Ld[r * (TB + 1) + k2 + 1] = v[u].y;
+            }
         }
         const double yj = (tid < TB) ? __ldcg(a.b + j0 + tid) : 0.0;  // y_j (from the factor kernel), fetched off the x chain
         double s = 0.0;
@@ -924,16 +933,42 @@ __global__ void __launch_bounds__(CT) chol_small_kernel(const double *__restrict
     __shared__ int sh_ok;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) sh_ok = 1;
-    for (int idx = tid; idx < TB * TB; idx += CT) {
-        const int r = idx >> 6, c = idx & 63;
-        double v = (c <= r) ? H[(size_t)r * ld + c] : 0.0;
-        if (r == c && r < n) v += (double)ep + (double)lm * (dampdiag ? dampdiag[r] : v);  // geom_kernels.cu:1176
-        A00[r * RS + c] = v;
-        if (T == 2) {
-            A10[r * RS + c] = H[(size_t)(TB + r) * ld + c];
-            double w = (c <= r) ? H[(size_t)(TB + r) * ld + TB + c] : 0.0;
-            if (r == c && TB + r < n) w += (double)ep + (double)lm * (dampdiag ? dampdiag[TB + r] : w);
-            A11[r * RS + c] = w;
+    {
+        // All loads of the (at most three) tiles leave before the first one is used: a load-use-store loop serialises on
+        // the trip to L2 (issue is in order), which was a third of this kernel's time at frontend size.
+        constexpr int U = TB * TB / 2 / CT;  // double2 per thread per tile
+        double2 v0[U], v1[U], v2[U];
+        double dd0[U], dd1[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int idx = tid + u * CT;
+            const int r = idx >> 5, c = (idx & 31) * 2;
+            v0[u] = __ldg(reinterpret_cast<const double2 *>(H + (size_t)r * ld + c));
+            const bool on_diag = (r == c || r == c + 1);
+            dd0[u] = (on_diag && dampdiag) ? __ldg(dampdiag + r) : 0.0;
+            if (T == 2) {
+                v1[u] = __ldg(reinterpret_cast<const double2 *>(H + (size_t)(TB + r) * ld + c));
+                v2[u] = __ldg(reinterpret_cast<const double2 *>(H + (size_t)(TB + r) * ld + TB + c));
+                dd1[u] = (on_diag && dampdiag) ? __ldg(dampdiag + TB + r) : 0.0;
+            }
+        }
+        auto damp = [&](double2 v, int r, int c, int row, double dd) {  // lower triangle + diag += ep + lm * diag (geom_kernels.cu:1176)
+            double x = (c <= r) ? v.x : 0.0, y = (c + 1 <= r) ? v.y : 0.0;
+            if (row < n) {
+                if (r == c) x += (double)ep + (double)lm * (dampdiag ? dd : x);
+                if (r == c + 1) y += (double)ep + (double)lm * (dampdiag ? dd : y);
+            }
+            return make_double2(x, y);
+        };
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int idx = tid + u * CT;
+            const int r = idx >> 5, c = (idx & 31) * 2;
+            *reinterpret_cast<double2 *>(A00 + r * RS + c) = damp(v0[u], r, c, r, dd0[u]);
+            if (T == 2) {
+                *reinterpret_cast<double2 *>(A10 + r * RS + c) = v1[u];
+                *reinterpret_cast<double2 *>(A11 + r * RS + c) = damp(v2[u], r, c, TB + r, dd1[u]);
+            }
         }
     }
     for (int i = tid; i < T * TB; i += CT) rhs[i] = b[i];

@@ -22,7 +22,6 @@ import torch.distributed as dist
 
 from . import _lib
 from .ext import slam_ext
-from .plan import cached_plan
 
 
 class PeerSystem:
@@ -131,8 +130,8 @@ def ba_sharded(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, 
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     t0, t1 = int(t0), int(t1)
     N, ht, wd = disps.shape
-    plan = cached_plan(ii.detach().to("cpu", torch.int64).contiguous(), jj.detach().to("cpu", torch.int64).contiguous(),
-                       N, ht, wd, t0, t1, rank, world)
+    # identity cache first: the same ii/jj tensor objects as last time => no device-to-host copy of the edge list
+    plan = slam_ext.ba_plan(ii, jj, N, ht, wd, t0, t1, rank, world)
     eng = engine_cls(plan, poses, disps, intrinsics, disps_sens, targets, weights, eta, motion_only)
     peer = None
     if world > 1 and engine_cls is CudaShardEngine and collective in ("auto", "nvls"):

@@ -39,18 +39,20 @@ def _check_dtype(dtype, **tensors):
 _LAST_PLAN: dict = {}
 
 
-def ba_plan(ii: torch.Tensor, jj: torch.Tensor, n_frames: int, ht: int, wd: int, t0: int, t1: int) -> BAPlan:
-    """Build (or fetch from the cache) the index bookkeeping for a graph; `ba` does this implicitly."""
+def ba_plan(ii: torch.Tensor, jj: torch.Tensor, n_frames: int, ht: int, wd: int, t0: int, t1: int, rank: int = 0,
+            world: int = 1) -> BAPlan:
+    """Build (or fetch from the cache) the index bookkeeping for a graph; `ba` does this implicitly.  `rank` / `world`:
+    the keyframe shard of a multi-GPU run (vipe_b200/distributed.py)."""
     import weakref
 
-    key = (int(n_frames), int(ht), int(wd), int(t0), int(t1))
+    key = (int(n_frames), int(ht), int(wd), int(t0), int(t1), int(rank), int(world))
     hit = _LAST_PLAN.get("entry")
     if hit is not None:
         r_ii, r_jj, v_ii, v_jj, k, plan = hit
         if r_ii() is ii and r_jj() is jj and ii._version == v_ii and jj._version == v_jj and k == key:
             return plan
     plan = cached_plan(ii.detach().to("cpu", torch.int64).contiguous(), jj.detach().to("cpu", torch.int64).contiguous(),
-                       n_frames, ht, wd, t0, t1)
+                       n_frames, ht, wd, t0, t1, int(rank), int(world))
     try:
         _LAST_PLAN["entry"] = (weakref.ref(ii), weakref.ref(jj), ii._version, jj._version, key, plan)
     except TypeError:

@@ -382,3 +382,30 @@ def test_host_feed_matches_direct_calls(slam_ext, dev):
         assert torch.allclose(p, wp, rtol=1e-5, atol=1e-6) and torch.allclose(d, wd, rtol=1e-5, atol=1e-6)
     with pytest.raises(RuntimeError):
         feed.run()  # nothing prefetched
+
+
+def test_zero_iterations_and_empty_graph(slam_ext, dev):
+    """Empty inputs: `iterations = 0` touches nothing; a graph without edges has a zero right-hand side, so one
+    iteration returns dx = 0, dz = 0 and leaves poses and disparities as they were."""
+    pr = make_problem("c1")
+    a = pr.args(dev)
+    a[11] = 0
+    dx, dz = slam_ext.ba(*a)
+    torch.cuda.synchronize()
+    assert torch.count_nonzero(dx) == 0 and torch.count_nonzero(dz) == 0
+    assert torch.equal(a[0].cpu(), pr.poses) and torch.equal(a[1].cpu(), pr.disps)
+
+    a = pr.args(dev)
+    ht, wd = pr.cfg.ht, pr.cfg.wd
+    a[4] = torch.zeros(0, 2, ht, wd, device=dev)
+    a[5] = torch.zeros(0, 2, ht, wd, device=dev)
+    a[7] = torch.zeros(0, dtype=torch.int64, device=dev)
+    a[8] = torch.zeros(0, dtype=torch.int64, device=dev)
+    K = pr.t1 - pr.t0  # kx = the window's frames when there are no edges
+    a[6] = a[6][:K].contiguous()
+    a[11] = 1
+    dx, dz = slam_ext.ba(*a)
+    torch.cuda.synchronize()
+    assert dx.shape == (K, 6) and torch.count_nonzero(dx) == 0
+    assert torch.count_nonzero(dz) == 0
+    assert torch.equal(a[0].cpu(), pr.poses) and torch.equal(a[1].cpu(), pr.disps)

@@ -458,8 +458,9 @@ extern "C" float *vipe_ba_debug_qw(const vipe_ba_plan *p, void *ws) { return (fl
 
 static int check_tensors(const vipe_ba_plan *p, const vipe_ba_tensors *t, int motion_only) {
     if (!p || !t) return fail("null plan/tensors");
-    if (!t->poses || !t->disps || !t->intrinsics || !t->targets || !t->weights || !t->dx_out)
-        return fail("null tensor pointer");
+    if (!t->poses || !t->disps || !t->intrinsics || !t->dx_out) return fail("null tensor pointer");
+    // a graph without edges has empty targets/weights, whose storage pointer is null
+    if (p->E > 0 && (!t->targets || !t->weights)) return fail("null tensor pointer");
     if (!motion_only && (!t->disps_sens || !t->eta || !t->dz_out)) return fail("disps_sens/eta/dz_out required unless motion_only");
     return 0;
 }

@@ -145,6 +145,14 @@ def _small_problem(seed, n_frames=7, ht=30, wd=41, t0=2, t1=None, stereo=True, d
     return pr, args
 
 
+def test_window_from_frame_zero(slam_ext, dev):
+    """t0 = 0: no pose is held fixed (the damping alone removes the gauge freedom) and the quirk Q4 of the reference --
+    the first pose of the window is skipped in the back-substitution -- hits frame 0 itself."""
+    pr, args = _small_problem(5, t0=0, stereo=False)
+    r = _compare(slam_ext, dev, pr, args_cpu=args)
+    assert r["te"] <= TOL_T and r["re"] <= TOL_R and r["de"] <= TOL_D, (r["te"], r["re"], r["de"])
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_irregular_graphs(slam_ext, dev, seed):
     pr, args = _small_problem(seed, t1=None if seed != 2 else 6)

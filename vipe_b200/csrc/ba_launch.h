@@ -28,8 +28,9 @@ cudaError_t launch_focal(const FocalArgs &a, int nframes, int dmax, cudaStream_t
 //   H: [npad x npad] fp64 row-major, lower triangle valid on entry (destroyed);  b: [npad] fp64 (destroyed)
 //   diag += ep + lm*diag (geom_kernels.cu:1176); factor; solve; dx[n] fp32.  Failure => dx = 0 (:1186-1188).
 // Returns the number of kernels launched through *launches.
-// `scratch` is chol_scratch_ints(npad) ints of device memory, zeroed once when the workspace is set up; `epoch` must be
-// a value never used before on this scratch (tile ready flags are epoch-valued so they need no per-solve reset).
+// `scratch` is chol_scratch_ints(npad) ints of device memory: tile ready flags, the words of the backward substitution's x
+// exchange and the fast copies of the factorised diagonal tiles (chol.cu).  The solve zeroes all of it itself with one
+// stream-ordered memset per call (zero = "not written yet" for the self-validating words); `epoch` is unused.
 cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx, int *scratch,
                                 double *dinv /*[npad]*/, double *linvT /*[npad/64][4096]*/,
                                 const double *dampdiag /*[npad] or null*/,

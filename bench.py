@@ -438,11 +438,14 @@ def main():
 
     feed = HostFeed(dev)
     if sharded:
-        e2e_fn = lambda *a: ba_sharded(*a, exchange=True, collective=args.collective)
+        from vipe_b200.plan import cached_plan
+
+        shard_plan = cached_plan(pr.ii.contiguous(), pr.jj.contiguous(), N, cfg.ht, cfg.wd, pr.t0, pr.t1, rank, world)
+        e2e_fn = lambda *a: ba_sharded(*a, exchange=True, collective=args.collective, plan=shard_plan)
     elif batched:
         e2e_fn = slam_ext.ba_batch
     else:
-        e2e_fn = slam_ext.ba
+        e2e_fn = None  # HostFeed's default: slam_ext.ba with the plan taken from the host copy of the edge list
     todo = list(zip(host_args, out_host))
 
     def e2e_run(nsteps):

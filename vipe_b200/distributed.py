@@ -114,7 +114,7 @@ class CudaShardEngine:
 
 
 def ba_sharded(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, t1, iterations, lm, ep,
-               motion_only, group=None, engine_cls=CudaShardEngine, exchange=True, profile=None, collective="auto"):
+               motion_only, group=None, engine_cls=CudaShardEngine, exchange=True, profile=None, collective="auto", plan=None):
     """`slam_ext.ba` sharded by source keyframe across the ranks of `group`.
 
     `collective`: "allreduce" = one NCCL all-reduce of the reduced camera system per iteration; "nvls" = no collective
@@ -130,8 +130,10 @@ def ba_sharded(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, 
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     t0, t1 = int(t0), int(t1)
     N, ht, wd = disps.shape
+    # `plan`: this rank's BAPlan if the caller already has it (e.g. built from a host copy of the edge list); else the
     # identity cache first: the same ii/jj tensor objects as last time => no device-to-host copy of the edge list
-    plan = slam_ext.ba_plan(ii, jj, N, ht, wd, t0, t1, rank, world)
+    if plan is None:
+        plan = slam_ext.ba_plan(ii, jj, N, ht, wd, t0, t1, rank, world)
     eng = engine_cls(plan, poses, disps, intrinsics, disps_sens, targets, weights, eta, motion_only)
     peer = None
     if world > 1 and engine_cls is CudaShardEngine and collective in ("auto", "nvls"):

@@ -36,7 +36,8 @@ def _check_dtype(dtype, **tensors):
 # objects are the ones seen last time (weak references still alive, hence not a recycled address) and their version
 # counters have not moved (no in-place write through torch since), the edge list is unchanged and the device-to-host
 # copy + hash -- a stream synchronisation per call -- can be skipped.
-_LAST_PLAN: dict = {}
+_LAST_PLANS: list = []  # most recent first; a few entries: callers that alternate between argument sets (HostFeed) hit too
+_LAST_PLANS_MAX = 4
 
 
 def ba_plan(ii: torch.Tensor, jj: torch.Tensor, n_frames: int, ht: int, wd: int, t0: int, t1: int, rank: int = 0,
@@ -46,17 +47,19 @@ def ba_plan(ii: torch.Tensor, jj: torch.Tensor, n_frames: int, ht: int, wd: int,
     import weakref
 
     key = (int(n_frames), int(ht), int(wd), int(t0), int(t1), int(rank), int(world))
-    hit = _LAST_PLAN.get("entry")
-    if hit is not None:
-        r_ii, r_jj, v_ii, v_jj, k, plan = hit
+    for pos, (r_ii, r_jj, v_ii, v_jj, k, plan) in enumerate(_LAST_PLANS):
         if r_ii() is ii and r_jj() is jj and ii._version == v_ii and jj._version == v_jj and k == key:
+            if pos:
+                _LAST_PLANS.insert(0, _LAST_PLANS.pop(pos))
             return plan
     plan = cached_plan(ii.detach().to("cpu", torch.int64).contiguous(), jj.detach().to("cpu", torch.int64).contiguous(),
                        n_frames, ht, wd, t0, t1, int(rank), int(world))
     try:
-        _LAST_PLAN["entry"] = (weakref.ref(ii), weakref.ref(jj), ii._version, jj._version, key, plan)
+        _LAST_PLANS.insert(0, (weakref.ref(ii), weakref.ref(jj), ii._version, jj._version, key, plan))
+        # entries whose tensors are gone can never hit again (and their addresses may be recycled)
+        _LAST_PLANS[:] = [e for e in _LAST_PLANS if e[0]() is not None and e[1]() is not None][:_LAST_PLANS_MAX]
     except TypeError:
-        _LAST_PLAN.pop("entry", None)
+        pass
     return plan
 
 
@@ -105,8 +108,12 @@ def validate(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj
     return dev, N, ht, wd, E
 
 
-def ba(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, t1, iterations, lm, ep, motion_only):
+def ba(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, t1, iterations, lm, ep, motion_only, plan=None):
     """Dense bundle adjustment; drop-in for `vipe.ext.slam_ext.ba` (csrc/slam_ext/slam.cpp:24-27).
+
+    `plan` (not in the reference's signature, optional): a BAPlan already built for exactly this edge list and window,
+    e.g. from the host copy of `ii/jj` (`HostFeed`); skips the lookup, which otherwise has to read the edge list back
+    from the device when it does not recognise the tensors.
 
     Runs `iterations` Gauss-Newton steps on the device without host synchronisation inside the loop, updates
     `poses[t0:t1]` and `disps[kx]` in place and returns `[dx, dz]` of the last iteration
@@ -115,7 +122,10 @@ def ba(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, 
     t0, t1, iterations = int(t0), int(t1), int(iterations)
     dev, N, ht, wd, E = validate(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, t1, motion_only)
     motion_only = bool(motion_only)
-    plan = ba_plan(ii, jj, N, ht, wd, t0, t1)  # one D2H of the edge list per call (the reference does >= 12 per iteration)
+    if plan is None:
+        plan = ba_plan(ii, jj, N, ht, wd, t0, t1)  # at most one D2H of the edge list per call (the reference does >= 12 per iteration)
+    elif (plan.E, plan.N, plan.ht, plan.wd, plan.t0, plan.t1) != (E, N, ht, wd, t0, t1):
+        raise RuntimeError("the plan passed to slam_ext.ba was built for another problem")
     K, HW, P = plan.K, ht * wd, t1 - t0
     dx = torch.zeros(P, 6, dtype=torch.float32, device=dev)
     dz = None

@@ -462,6 +462,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     e2e_run(e2e_steps)
+    torch.cuda.current_stream().wait_event(feed.last_done)  # the last step's read-back (third stream) is inside the timed region
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)

@@ -385,7 +385,7 @@ def test_host_feed_matches_direct_calls(slam_ext, dev):
         if q + 1 < len(host):
             feed.prefetch(host[q + 1])
         feed.run(out_poses=outs[q][0], out_disps=outs[q][1])
-    torch.cuda.synchronize()
+    feed.synchronize()
     for (p, d), (wp, wd) in zip(outs, want):
         assert torch.allclose(p, wp, rtol=1e-5, atol=1e-6) and torch.allclose(d, wd, rtol=1e-5, atol=1e-6)
     with pytest.raises(RuntimeError):

@@ -25,7 +25,8 @@ class HostFeed:
             (dx, dz), dev_args = feed.run(out_poses=..., out_disps=...)   # current stream
 
     `run` makes the current stream wait for the upload, calls `fn` (default `slam_ext.ba`) on the device copies and, if
-    host output tensors are given, reads the updated poses / disparities back (asynchronously, on the current stream).
+    host output tensors are given, reads the updated poses / disparities back on a third stream (`synchronize()` waits
+    for them).
     A slot is reused only after the call that consumed it -- including its read-back -- has finished on the device."""
 
     def __init__(self, device, slots: int = 2):
@@ -33,6 +34,7 @@ class HostFeed:
         if self.dev.type != "cuda":
             raise RuntimeError("HostFeed needs a CUDA device (vipe_b200 has no CPU fallback)")
         self.copy_stream = torch.cuda.Stream(self.dev)
+        self.down_stream = torch.cuda.Stream(self.dev)  # results go back on their own stream: the next solve does not wait for them
         self._slots = [None] * slots
         self._free = [None] * slots
         self._ready = []
@@ -86,11 +88,22 @@ class HostFeed:
         cur = torch.cuda.current_stream(self.dev)
         cur.wait_event(ev)
         res = fn(*a) if fn is not None else slam_ext.ba(*a, plan=plan)
-        if out_poses is not None:
-            out_poses.copy_(a[0], non_blocking=True)
-        if out_disps is not None:
-            out_disps.copy_(a[1], non_blocking=True)
         done = torch.cuda.Event()
         done.record(cur)
-        self._free[b] = done
+        if out_poses is not None or out_disps is not None:
+            with torch.cuda.stream(self.down_stream):
+                self.down_stream.wait_event(done)
+                if out_poses is not None:
+                    out_poses.copy_(a[0], non_blocking=True)
+                if out_disps is not None:
+                    out_disps.copy_(a[1], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(self.down_stream)
+        self._free[b] = done  # the slot is reused only after its results have left
+        self.last_done = done
         return res, a
+
+    def synchronize(self):
+        """Block until the results of every `run` so far are in their host tensors."""
+        self.down_stream.synchronize()
+        torch.cuda.current_stream(self.dev).synchronize()

@@ -9,6 +9,11 @@
 // The right-hand side rides along as one extra tile row (forward substitution for free); a second dataflow
 // kernel does the backward substitution.  Claim order respects the dependencies, so every spin-wait is on a tile
 // that a resident CTA is already working on: no cooperative launch is needed.
+// At backend sizes the solve is bound by the latency of the chain of diagonal tiles (potrf -> tile solve -> update ->
+// potrf ...), so the hops on that chain avoid flags and fences: the factorised diagonal tile and the backward
+// substitution's x travel as self-validating 8-byte words (zero = not written yet), the diagonal tile in two halves so
+// that its readers start their tile solve while the second half is still being factorised (see "self-validating
+// exchange" below).  Everything not on that chain uses the ordinary ready flags.
 // A non-positive (or NaN) pivot raises *fail and the solve writes dx = 0, like the reference (:1186-1188).
 #include <type_traits>
 
@@ -447,11 +452,8 @@ __device__ __noinline__ void tile_trsm_mma_t(double *X, const double *L, const d
     }
     __syncthreads();
 }
-__device__ __forceinline__ void tile_trsm_mma(double *X, const double *L, const double *dinv, double *linv8, double *tmp,
-                                              int nblk = 8, int nrw = 8) {
-    (void)nrw;
-    if (nblk == 4) tile_trsm_mma_t<4>(X, L, dinv, linv8, tmp);
-    else tile_trsm_mma_t<8>(X, L, dinv, linv8, tmp);
+__device__ __forceinline__ void tile_trsm_mma(double *X, const double *L, const double *dinv, double *linv8, double *tmp) {
+    tile_trsm_mma_t<8>(X, L, dinv, linv8, tmp);
 }
 
 // X <- X L_jj^-T with L_jj taken from its fast copy `ft` as the two halves arrive (see fast_half_store): same right-looking

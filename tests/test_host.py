@@ -140,3 +140,25 @@ def test_host_feed_needs_cuda():
 
     with pytest.raises(RuntimeError):
         HostFeed("cpu")
+
+
+def test_identity_plan_cache_keeps_several_graphs(lib_built):
+    """Callers that alternate between argument sets (HostFeed's two slots, frontend/backend graphs) must all hit the
+    identity cache; an in-place edit of the edge list must miss it."""
+    from vipe_b200.ext import slam_ext
+
+    gen = torch.Generator().manual_seed(7)
+    graphs = [_random_graph(gen, 9, 20) for _ in range(3)]
+    plans = [slam_ext.ba_plan(ii, jj, 9, 8, 8, 1, 9) for ii, jj in graphs]
+    for _ in range(2):
+        for (ii, jj), p in zip(graphs, plans):
+            assert slam_ext.ba_plan(ii, jj, 9, 8, 8, 1, 9) is p
+    assert len(slam_ext._LAST_PLANS) <= slam_ext._LAST_PLANS_MAX
+    ii, jj = graphs[0]
+    keep = int(jj[0])
+    jj[0] = (keep + 1) % 9 if (keep + 1) % 9 != int(ii[0]) else (keep + 2) % 9
+    p2 = slam_ext.ba_plan(ii, jj, 9, 8, 8, 1, 9)
+    assert p2 is not plans[0]
+    # a shard's plan is its own entry
+    assert slam_ext.ba_plan(ii, jj, 9, 8, 8, 1, 9, 1, 2) is not p2
+    assert slam_ext.ba_plan(ii, jj, 9, 8, 8, 1, 9, 1, 2) is slam_ext.ba_plan(ii, jj, 9, 8, 8, 1, 9, 1, 2)

@@ -41,35 +41,65 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled during the timed region (B200_PROFILING.md recipe): NVML every 20 ms where
+    the bindings load (the device-timed region lasts ~0.1 s; one `nvidia-smi` process start takes longer than that),
+    else `nvidia-smi` every 0.2 s."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        self.nvml, self.handle, self.source = None, None, "nvidia-smi"
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # torch's device index follows CUDA_VISIBLE_DEVICES; NVML's does not
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        bits = [n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
+                n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap]
+        return [str(sm), str(mx), "", *["Active" if r & b else "Not Active" for b in bits]]
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.02 if self.nvml is not None else 0.2)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=3)
         sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
         mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples if len(s) >= 7 for i in range(4) if s[3 + i].lower().startswith("active")})
+        reasons = sorted({self.NAMES[i] for s in self.samples if len(s) >= 7 for i in range(4) if s[3 + i].lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples), "source": self.source}
 
 
 def algorithmic_bytes(cfg, E, K, N, HW, motion_only):
@@ -318,7 +348,6 @@ def main():
         ev[s][1].record()
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
     launches = sum(pl.launch_count for pl in plans) * args.steps if plans else None
     # per-stage times come from a separate, untimed pass: stage events switch the CUDA-graph replay off
     for pl in plans:
@@ -471,6 +500,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_value = e2e_steps * cfg.iters * clips / (e2e_ms / 1e3)
+    # the sampler ran from the start of the timed region to the end of the end-to-end leg (the device-timed region alone
+    # lasts ~0.1 s, one or two nvidia-smi samples)
+    clocks = sampler.stop()
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

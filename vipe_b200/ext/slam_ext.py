@@ -148,6 +148,7 @@ def ba(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, 
 
 
 _BATCH_PLANS: dict = {}
+_BATCH_LAST: dict = {}
 
 
 def ba_batch(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, frame_ptr, t0s, t1s, iterations, lm, ep,
@@ -158,18 +159,34 @@ def ba_batch(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj
     concatenation of the per-clip arguments of `ba` (poses[sum N,7], disps[sum N,ht,wd], targets[sum E,2,ht,wd], ...;
     `ii/jj` hold GLOBAL frame ids); problem c owns frames `[frame_ptr[c], frame_ptr[c+1])` and optimises its window
     `[t0s[c], t1s[c])`.  Every problem behaves exactly like its own `ba` call.  Returns `[dx[sum P,6], dz[K,ht*wd]]`."""
+    import weakref
+
     dev, N, ht, wd, E = validate(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, 0, 0, motion_only)
     motion_only = bool(motion_only)
     fp = torch.as_tensor(frame_ptr, dtype=torch.int64).cpu()
     t0s_h = torch.as_tensor(t0s, dtype=torch.int64).cpu()
     t1s_h = torch.as_tensor(t1s, dtype=torch.int64).cpu()
-    ii_h, jj_h = ii.detach().to("cpu", torch.int64).contiguous(), jj.detach().to("cpu", torch.int64).contiguous()
-    key = (ii_h.numpy().tobytes(), jj_h.numpy().tobytes(), fp.numpy().tobytes(), t0s_h.numpy().tobytes(), t1s_h.numpy().tobytes(), N, ht, wd)
-    plan = _BATCH_PLANS.get(key)
+    small = (fp.numpy().tobytes(), t0s_h.numpy().tobytes(), t1s_h.numpy().tobytes(), N, ht, wd)
+    # identity fast path, as in ba_plan: the same ii/jj objects, unwritten since, with the same windows => same plan,
+    # without reading the edge list back from the device (a stream synchronisation per call)
+    plan = None
+    hit = _BATCH_LAST.get("entry")
+    if hit is not None:
+        r_ii, r_jj, v_ii, v_jj, k, p_hit = hit
+        if r_ii() is ii and r_jj() is jj and ii._version == v_ii and jj._version == v_jj and k == small:
+            plan = p_hit
     if plan is None:
-        if len(_BATCH_PLANS) >= 4:
-            _BATCH_PLANS.pop(next(iter(_BATCH_PLANS)))
-        plan = _BATCH_PLANS[key] = BAPlan(ii_h, jj_h, N, ht, wd, 0, 0, batch=(fp, t0s_h, t1s_h))
+        ii_h, jj_h = ii.detach().to("cpu", torch.int64).contiguous(), jj.detach().to("cpu", torch.int64).contiguous()
+        key = (ii_h.numpy().tobytes(), jj_h.numpy().tobytes(), *small)
+        plan = _BATCH_PLANS.get(key)
+        if plan is None:
+            if len(_BATCH_PLANS) >= 4:
+                _BATCH_PLANS.pop(next(iter(_BATCH_PLANS)))
+            plan = _BATCH_PLANS[key] = BAPlan(ii_h, jj_h, N, ht, wd, 0, 0, batch=(fp, t0s_h, t1s_h))
+        try:
+            _BATCH_LAST["entry"] = (weakref.ref(ii), weakref.ref(jj), ii._version, jj._version, small, plan)
+        except TypeError:
+            _BATCH_LAST.pop("entry", None)
     K, HW, P = plan.K, ht * wd, plan.P
     dx = torch.zeros(P, 6, dtype=torch.float32, device=dev)
     dz = None

@@ -241,3 +241,12 @@ def pose_errors(p, p_ref, t0, t1):
 def disp_error(d, d_ref, kx):
     a, b = d[kx].double().cpu(), d_ref[kx].double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def disp_error_p999(d, d_ref, kx):
+    """99.9th percentile over the pixels of the frames in `kx` of |d - d_ref| / |d_ref| (reported
+    beside the Frobenius figure, which a handful of bad pixels could hide behind)."""
+    a, b = d[kx].double().cpu().flatten(), d_ref[kx].double().cpu().flatten()
+    rel = (a - b).abs() / b.abs().clamp_min(1e-12)
+    k = max(1, int(round(0.999 * rel.numel())))
+    return float(rel.kthvalue(k).values)

@@ -2,6 +2,7 @@
 // graph), workspace layout, and the stream-ordered Gauss-Newton loop.  No torch, no allocation, no sync.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -28,6 +29,19 @@ int set_last_error(const char *msg) { return fail(msg ? msg : "unknown error"); 
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+static int device_sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached_dev = dev;
+        cached = n;
+    }
+    return cached;
+}
+
 struct vipe_ba_plan {
     int64_t E = 0, N = 0;
     int ht = 0, wd = 0, HW = 0, t0 = 0, t1 = 0, P = 0, K = 0;
@@ -37,6 +51,12 @@ struct vipe_ba_plan {
     bool packed = false;  // linearize2 (pixel-pair) kernel
     int NTm = 256, PPTm = 1, ntile_m = 0;  // motion-only tile shape (no staging buffer => always the widest)
     int k_lo = 0, k_hi = 0, dmax = 0;
+    // owned frames by linearisation kernel: the tensor-core pipeline (ba_lin3.cu) takes 1 <= degree <= kLin3MaxDeg, the rest
+    // (no edges, or more edges than its operand tile holds) stay with the frame-major FMA kernel
+    std::vector<int> flist_tc, flist_rest;
+    int dmax_rest = 0;
+    bool use_lin3 = false;
+    size_t off_flist_tc = 0, off_flist_rest = 0;
     int64_t n_triples = 0;
     std::vector<int64_t> kx, kk_exp;
     std::vector<int> kx32, fptr, fedge, e_jj;
@@ -290,6 +310,20 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
         return fail("a source frame has too many outgoing edges for the shared-memory staging buffer");
     }
     p->ntile = (p->HW + p->NT * p->PPT - 1) / (p->NT * p->PPT);
+    {
+        const char *env = std::getenv("VIPE_BA_LIN3");
+        const bool want = !(env && env[0] == '0');
+        p->use_lin3 = want && p->packed && lin3_supported(p->HW, p->NT * p->PPT);
+        for (int k = p->k_lo; k < p->k_hi; k++) {
+            const int d = p->fptr[k + 1] - p->fptr[k];
+            if (p->use_lin3 && d >= 1 && d <= kLin3MaxDeg) {
+                p->flist_tc.push_back(k);
+            } else {
+                p->flist_rest.push_back(k);
+                p->dmax_rest = std::max(p->dmax_rest, d);
+            }
+        }
+    }
     // motion-only shares the partial layout (ntile), so it uses the same tile shape
     p->NTm = p->NT;
     p->PPTm = p->PPT;
@@ -327,6 +361,8 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     p->off_pn = take(sizeof(int) * C);
     p->off_prow0 = take(sizeof(int) * C);
     p->off_pn_focal = take(sizeof(int) * C);
+    p->off_flist_tc = take(sizeof(int) * std::max<size_t>(p->flist_tc.size(), 1));
+    p->off_flist_rest = take(sizeof(int) * std::max<size_t>(p->flist_rest.size(), 1));
     p->idx_bytes = off;
     p->ntile_f = focal_tiles(p->HW);
     p->off_fpart = take(sizeof(float) * (size_t)std::max<int64_t>(E, 1) * p->ntile_f * kFocalStride);
@@ -359,6 +395,9 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     std::memcpy(p->blob.data() + p->off_pnpad, p->prob_npad.data(), sizeof(int) * C);
     std::memcpy(p->blob.data() + p->off_pn, p->prob_n.data(), sizeof(int) * C);
     std::memcpy(p->blob.data() + p->off_prow0, p->prob_row0.data(), sizeof(int) * C);
+    if (!p->flist_tc.empty()) std::memcpy(p->blob.data() + p->off_flist_tc, p->flist_tc.data(), sizeof(int) * p->flist_tc.size());
+    if (!p->flist_rest.empty())
+        std::memcpy(p->blob.data() + p->off_flist_rest, p->flist_rest.data(), sizeof(int) * p->flist_rest.size());
     {
         std::vector<int> nf(p->prob_n);
         for (auto &v : nf) v += 1;
@@ -493,11 +532,25 @@ static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void 
     la.gpart = (float *)(w + p->off_gpart);
     la.qbuf = (float *)(w + p->off_q);
     la.qwbuf = (float *)(w + p->off_qw);
-    if (p->packed)
-        VBA_CUDA(launch_linearize2(la, nframes, std::max(p->dmax, 1), motion_only != 0, p->NT, st));
-    else
-        VBA_CUDA(launch_linearize(la, nframes, std::max(p->dmax, 1), motion_only != 0, p->NT, p->PPT, st));
-    p->launches++;
+    if (p->packed && !motion_only && p->use_lin3) {
+        // two launches over disjoint frame lists: tensor-core pipeline for the low-degree frames, FMA kernel for the rest
+        if (!p->flist_tc.empty()) {
+            VBA_CUDA(launch_lin3(la, (const int *)(w + p->off_flist_tc), (int)p->flist_tc.size(), p->NT * p->PPT, device_sm_count(), st));
+            p->launches++;
+        }
+        if (!p->flist_rest.empty()) {
+            la.flist = (const int *)(w + p->off_flist_rest);
+            VBA_CUDA(launch_linearize2(la, (int)p->flist_rest.size(), std::max(p->dmax_rest, 1), false, p->NT, st));
+            la.flist = nullptr;
+            p->launches++;
+        }
+    } else {
+        if (p->packed)
+            VBA_CUDA(launch_linearize2(la, nframes, std::max(p->dmax, 1), motion_only != 0, p->NT, st));
+        else
+            VBA_CUDA(launch_linearize(la, nframes, std::max(p->dmax, 1), motion_only != 0, p->NT, p->PPT, st));
+        p->launches++;
+    }
     if (p->opt.optimize_focal) {
         FocalArgs fa;
         fa.tb = la.tb;

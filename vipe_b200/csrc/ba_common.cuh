@@ -81,6 +81,7 @@ struct LinArgs {
     float *gpart;  // per frame: [ntile][npairs*36 + 6*d]
     float *qbuf;   // [K][HW]  Q = 1/C
     float *qwbuf;  // [K][HW]  Q*w
+    const int *flist = nullptr;  // DEV: kx positions of the frames this launch covers (null: k_lo + blockIdx.y)
 };
 
 constexpr int kFocalNT = 256;     // the focal pass tiles a frame into 256-pixel tiles of its own

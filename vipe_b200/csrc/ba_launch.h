@@ -14,6 +14,11 @@ cudaError_t launch_linearize(const LinArgs &a, int nframes, int dmax, bool motio
 // packed 2-pixels-per-thread variant (ba_linearize2.cu); needs an even HW.  TILE = 2 * NT.
 bool tile_config2(int HW, int dmax, bool motion, int &NT);
 cudaError_t launch_linearize2(const LinArgs &a, int nframes, int dmax, bool motion, int NT, cudaStream_t st);
+// Blackwell pipeline (ba_lin3.cu): TMA ring + tcgen05 Gram for frames with 1 <= out-degree <= kLin3MaxDeg; `flist_dev` lists
+// the kx positions of those frames, `chunk_px` is the pixel span of one partial record (= the plan's tile size).
+constexpr int kLin3MaxDeg = 10;
+bool lin3_supported(int HW, int chunk_px);
+cudaError_t launch_lin3(const LinArgs &a, const int *flist_dev, int nframes, int chunk_px, int num_sms, cudaStream_t st);
 cudaError_t launch_frame_reduce(const ReduceArgs &a, int nframes, int dmax, cudaStream_t st);
 cudaError_t launch_backsub(const BackArgs &a, int nframes, int dmax, cudaStream_t st);
 // `intr` non-null: also apply the focal step dx[focal_row] * focal_jscale to fx and fy

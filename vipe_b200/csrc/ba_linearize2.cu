@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(2 * NT, (MOTION && NT == 256) ? 2 : 1) lineari
     extern __shared__ __align__(16) float smem[];
     const Tables &tb = a.tb;
     const int tile = blockIdx.x;
-    const int k = tb.k_lo + blockIdx.y;
+    const int k = a.flist ? a.flist[blockIdx.y] : tb.k_lo + blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int half = tid / NT, slot = tid - half * NT, wh = slot >> 5;
     const int src = tb.kx[k];

@@ -45,6 +45,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_verbose: bool = Fals
     flags = ["-O3", "-std=c++17", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC", f"-I{PKG.parent / 'include'}"]
     if ptxas_verbose:
         flags += ["-Xptxas", "-v"]
+    flags += [f"-D{d}" for d in os.environ.get("VIPE_BA_DEFINES", "").split() if d]  # developer switches, e.g. VBA_LIN3_TRACE
 
     def compile_one(src: str):
         obj = LIB / (Path(src).stem + ".o")

@@ -49,6 +49,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
+// for roles that expect to wait long (producer, MMA issuer, flush warps): back off between polls so that the polling
+// does not take issue slots and shared-memory-pipe bandwidth from the warps doing the work
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(64);
+        if ((++spins & 255u) == 0 && clock64() - t0 > 8000000000LL) mbar_timeout(bar, parity);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ bulk copy (TMA, 1-D)
 // global -> shared, completion counted in bytes on `bar`.  dst, src 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {

@@ -55,8 +55,10 @@ struct vipe_ba_plan {
     // (no edges, or more edges than its operand tile holds) stay with the frame-major FMA kernel
     std::vector<int> flist_tc, flist_rest;
     int dmax_rest = 0;
-    bool use_lin3 = false;
-    size_t off_flist_tc = 0, off_flist_rest = 0;
+    bool use_lin3 = false, use_lin3_full = false;
+    size_t off_flist_tc = 0, off_flist_rest = 0, off_lin3_items = 0, off_econst = 0, off_slot_src = 0;
+    std::vector<int> slot_src;
+    std::vector<Lin3Item> lin3_items;
     int64_t n_triples = 0;
     std::vector<int64_t> kx, kk_exp;
     std::vector<int> kx32, fptr, fedge, e_jj;
@@ -311,12 +313,16 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     }
     p->ntile = (p->HW + p->NT * p->PPT - 1) / (p->NT * p->PPT);
     {
+        // VIPE_BA_LIN3: "0" = frame-major FMA kernels only; "1" (default) = the TMA-fed motion-only pipeline; "2" = also the
+        // tensor-core pipeline for the full linearisation of frames with <= kLin3MaxDeg edges (parity-tested, but measured no
+        // faster than the FMA kernel on B200: both run at ~0.106 us per edge at C3)
         const char *env = std::getenv("VIPE_BA_LIN3");
-        const bool want = !(env && env[0] == '0');
-        p->use_lin3 = want && p->packed && lin3_supported(p->HW, p->NT * p->PPT);
+        const int mode = env ? std::atoi(env) : 1;
+        p->use_lin3 = mode >= 1 && p->packed && lin3_supported(p->HW, p->NT * p->PPT);
+        p->use_lin3_full = p->use_lin3 && mode >= 2;
         for (int k = p->k_lo; k < p->k_hi; k++) {
             const int d = p->fptr[k + 1] - p->fptr[k];
-            if (p->use_lin3 && d >= 1 && d <= kLin3MaxDeg) {
+            if (p->use_lin3_full && d >= 1 && d <= kLin3MaxDeg) {
                 p->flist_tc.push_back(k);
             } else {
                 p->flist_rest.push_back(k);
@@ -361,10 +367,27 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     p->off_pn = take(sizeof(int) * C);
     p->off_prow0 = take(sizeof(int) * C);
     p->off_pn_focal = take(sizeof(int) * C);
+    {
+        const int chunk_px = p->NT * p->PPT, nchunk = chunk_px > 0 ? p->HW / chunk_px : 0;
+        for (int k : p->flist_tc)
+            for (int ch = 0; ch < nchunk; ch++) {
+                Lin3Item it;
+                it.k = k, it.src = p->kx32[k], it.s0 = p->fptr[k], it.d = p->fptr[k + 1] - p->fptr[k];
+                it.px0 = ch * chunk_px, it.chunk = ch;
+                for (int m = 0; m < kLin3MaxDeg; m++) it.edge[m] = m < it.d ? p->fedge[it.s0 + m] : -1;
+                p->lin3_items.push_back(it);
+            }
+    }
+    p->off_lin3_items = take(sizeof(Lin3Item) * std::max<size_t>(p->lin3_items.size(), 1));
+    p->slot_src.assign(std::max<int64_t>(E, 1), 0);
+    for (int k = 0; k < K; k++)
+        for (int s2 = p->fptr[k]; s2 < p->fptr[k + 1]; s2++) p->slot_src[s2] = p->kx32[k];
+    p->off_slot_src = take(sizeof(int) * p->slot_src.size());
     p->off_flist_tc = take(sizeof(int) * std::max<size_t>(p->flist_tc.size(), 1));
     p->off_flist_rest = take(sizeof(int) * std::max<size_t>(p->flist_rest.size(), 1));
     p->idx_bytes = off;
     p->ntile_f = focal_tiles(p->HW);
+    p->off_econst = take(sizeof(float) * 16 * (p->use_lin3 ? (size_t)std::max<int64_t>(E, 1) : 1));
     p->off_fpart = take(sizeof(float) * (size_t)std::max<int64_t>(E, 1) * p->ntile_f * kFocalStride);
     p->off_ffpart = take(sizeof(float) * (size_t)K * p->ntile_f * 2);
     p->off_uf = take(sizeof(float) * (size_t)K * p->HW);
@@ -395,6 +418,9 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     std::memcpy(p->blob.data() + p->off_pnpad, p->prob_npad.data(), sizeof(int) * C);
     std::memcpy(p->blob.data() + p->off_pn, p->prob_n.data(), sizeof(int) * C);
     std::memcpy(p->blob.data() + p->off_prow0, p->prob_row0.data(), sizeof(int) * C);
+    std::memcpy(p->blob.data() + p->off_slot_src, p->slot_src.data(), sizeof(int) * p->slot_src.size());
+    if (!p->lin3_items.empty())
+        std::memcpy(p->blob.data() + p->off_lin3_items, p->lin3_items.data(), sizeof(Lin3Item) * p->lin3_items.size());
     if (!p->flist_tc.empty()) std::memcpy(p->blob.data() + p->off_flist_tc, p->flist_tc.data(), sizeof(int) * p->flist_tc.size());
     if (!p->flist_rest.empty())
         std::memcpy(p->blob.data() + p->off_flist_rest, p->flist_rest.data(), sizeof(int) * p->flist_rest.size());
@@ -532,11 +558,12 @@ static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void 
     la.gpart = (float *)(w + p->off_gpart);
     la.qbuf = (float *)(w + p->off_q);
     la.qwbuf = (float *)(w + p->off_qw);
-    if (p->packed && !motion_only && p->use_lin3) {
+    if (p->packed && !motion_only && p->use_lin3_full) {
         // two launches over disjoint frame lists: tensor-core pipeline for the low-degree frames, FMA kernel for the rest
         if (!p->flist_tc.empty()) {
-            VBA_CUDA(launch_lin3(la, (const int *)(w + p->off_flist_tc), (int)p->flist_tc.size(), p->NT * p->PPT, device_sm_count(), st));
-            p->launches++;
+            VBA_CUDA(launch_lin3(la, (const Lin3Item *)(w + p->off_lin3_items), (int)p->flist_tc.size(), p->NT * p->PPT,
+                                 (float *)(w + p->off_econst), device_sm_count(), st));
+            p->launches += 2;
         }
         if (!p->flist_rest.empty()) {
             la.flist = (const int *)(w + p->off_flist_rest);
@@ -544,6 +571,11 @@ static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void 
             la.flist = nullptr;
             p->launches++;
         }
+    } else if (p->packed && motion_only && p->use_lin3) {
+        const int slot_lo = p->fptr[p->k_lo], nslots = p->fptr[p->k_hi] - slot_lo;
+        VBA_CUDA(launch_lin3_motion(la, (const int *)(w + p->off_slot_src), slot_lo, nslots, p->NT * p->PPT, (float *)(w + p->off_econst),
+                                    device_sm_count(), st));
+        p->launches += 2;
     } else {
         if (p->packed)
             VBA_CUDA(launch_linearize2(la, nframes, std::max(p->dmax, 1), motion_only != 0, p->NT, st));

@@ -14,11 +14,20 @@ cudaError_t launch_linearize(const LinArgs &a, int nframes, int dmax, bool motio
 // packed 2-pixels-per-thread variant (ba_linearize2.cu); needs an even HW.  TILE = 2 * NT.
 bool tile_config2(int HW, int dmax, bool motion, int &NT);
 cudaError_t launch_linearize2(const LinArgs &a, int nframes, int dmax, bool motion, int NT, cudaStream_t st);
-// Blackwell pipeline (ba_lin3.cu): TMA ring + tcgen05 Gram for frames with 1 <= out-degree <= kLin3MaxDeg; `flist_dev` lists
-// the kx positions of those frames, `chunk_px` is the pixel span of one partial record (= the plan's tile size).
+// Blackwell pipeline (ba_lin3.cu): TMA stages + tcgen05 Gram for frames with 1 <= out-degree <= kLin3MaxDeg.  The plan lists
+// its work as items (frame, chunk of `chunk_px` pixels = one partial record), frame-major; `econst_dev` is E x 16 floats of
+// scratch for the per-edge constants.
 constexpr int kLin3MaxDeg = 10;
+struct Lin3Item {
+    int k, src, s0, d, px0, chunk;  // kx position, frame id, first edge slot, out-degree, first pixel, chunk index
+    int edge[kLin3MaxDeg];          // edge ids, -1 beyond d
+};
 bool lin3_supported(int HW, int chunk_px);
-cudaError_t launch_lin3(const LinArgs &a, const int *flist_dev, int nframes, int chunk_px, int num_sms, cudaStream_t st);
+cudaError_t launch_lin3(const LinArgs &a, const Lin3Item *items_dev, int nframes, int chunk_px, float *econst_dev, int num_sms,
+                        cudaStream_t st);
+// motion-only variant: flat (edge slot, chunk) units over the slots [slot_lo, slot_lo + nslots); `slot_src_dev[slot]` = source frame id
+cudaError_t launch_lin3_motion(const LinArgs &a, const int *slot_src_dev, int slot_lo, int nslots, int chunk_px, float *econst_dev,
+                               int num_sms, cudaStream_t st);
 cudaError_t launch_frame_reduce(const ReduceArgs &a, int nframes, int dmax, cudaStream_t st);
 cudaError_t launch_backsub(const BackArgs &a, int nframes, int dmax, cudaStream_t st);
 // `intr` non-null: also apply the focal step dx[focal_row] * focal_jscale to fx and fy

@@ -24,14 +24,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the time hint (ns) runs out, so a waiting warp
+// takes (almost) no issue slots
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
         : "memory");
     return ok != 0;
 }
@@ -56,7 +58,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity
     const long long t0 = clock64();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(64);
+        __nanosleep(200);
         if ((++spins & 255u) == 0 && clock64() - t0 > 8000000000LL) mbar_timeout(bar, parity);
     }
 }
@@ -136,15 +138,12 @@ __device__ __forceinline__ void mma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// fp32 -> (hi, lo) with hi exactly representable in tf32 (round to nearest) and lo = x - hi rounded to tf32
+// fp32 -> (hi, lo): hi = x rounded to tf32's 10 mantissa bits (round half away, two integer ops; cvt.rna.tf32 is emulated
+// with a dozen), lo = x - hi exactly (<= 13 significant bits, of which the tensor core keeps the leading 11:
+// 2^-22 |x| relative).  Finite inputs only.
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
-    const float r = x - hi;
-    uint32_t l;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
-    lo = __uint_as_float(l);
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    lo = x - hi;
 }
 
 }  // namespace sm100

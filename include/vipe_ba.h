@@ -73,6 +73,11 @@ int vipe_ba_plan_copy_csr(const vipe_ba_plan *plan, int64_t *ptrs_out, int64_t *
 /* Owned kx positions [lo, hi) of this rank, and of any rank. */
 int vipe_ba_plan_owned_range(const vipe_ba_plan *plan, int rank, int64_t *lo, int64_t *hi);
 /* Number of (pose_a, pose_b, frame) triples schur_block would enumerate (:1225-1240); bookkeeping check. */
+/* Position of every free pose in the reduced camera system, out[t1 - t0] in pose order: unknowns 6*out[p] .. 6*out[p]+5 of
+ * vipe_ba_system_buffer() belong to pose t0 + p.  Today this is the natural order (a fill-reducing pose order does not
+ * survive the solver's 64 x 64 tiling); callers that read the system should go through it anyway.
+ * dx is always returned in pose order. */
+int vipe_ba_plan_copy_sys_order(const vipe_ba_plan *plan, int64_t *out);
 int64_t vipe_ba_plan_num_schur_triples(const vipe_ba_plan *plan);
 /* Largest number of edges leaving one owned source frame. */
 int vipe_ba_plan_max_degree(const vipe_ba_plan *plan);

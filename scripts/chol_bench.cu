@@ -210,7 +210,7 @@ int main(int argc, char **argv) {
         cudaDeviceSynchronize();
         int cnt = 0;
         cudaEventRecord(e0);
-        cudaError_t err = launch_damped_solve(dH, dH + (size_t)npad * npad, n, npad, 0.0f, 0.0f, ddx, dscr, ddinv, ddinv + npad, nullptr, nullptr, r + 1, 0, &cnt);
+        cudaError_t err = launch_damped_solve(dH, dH + (size_t)npad * npad, n, npad, 0.0f, 0.0f, ddx, dscr, ddinv, ddinv + npad, nullptr, nullptr, r + 1, nullptr, nullptr, 0, &cnt);
         cudaEventRecord(e1);
         cudaDeviceSynchronize();
         if (err != cudaSuccess || cudaGetLastError() != cudaSuccess) { printf("cuda error %s\n", cudaGetErrorString(err)); return 1; }

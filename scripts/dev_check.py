@@ -29,10 +29,11 @@ def stage_check(pr, motion_only=False):
     torch.cuda.synchronize()
     sysv, npad = plan.system_view(ws)
     H = sysv[: npad * npad].view(npad, npad).cpu()
-    b = sysv[npad * npad:].cpu()
     n = 6 * P
-    Hl = torch.tril(H[:n, :n])
-    Hfull = Hl + torch.tril(Hl, -1).T
+    idx = plan.system_index()  # the system is stored in the plan's elimination order
+    Hl = torch.tril(H)
+    Hfull = (Hl + torch.tril(Hl, -1).T)[idx][:, idx]
+    b = sysv[npad * npad:].cpu()[idx]
 
     # oracle, one iteration
     o = pr.args()

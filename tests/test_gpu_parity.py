@@ -101,9 +101,11 @@ def test_stage_outputs_match_oracle(slam_ext, dev):
     torch.cuda.synchronize()
     sysv, npad = plan.system_view(ws)
     n = 6 * plan.P
-    H = sysv[: npad * npad].view(npad, npad).cpu()[:n, :n]
-    H = torch.tril(H) + torch.tril(H, -1).T
-    b = sysv[npad * npad:].cpu()[:n]
+    Hs = sysv[: npad * npad].view(npad, npad).cpu()
+    Hs = torch.tril(Hs) + torch.tril(Hs, -1).T
+    idx = plan.system_index()  # the system is stored in the plan's elimination order
+    H = Hs[idx][:, idx]
+    b = sysv[npad * npad:].cpu()[idx]
     o = pr.args()
     o[11] = 1
     tr = O.Trace()

@@ -26,6 +26,7 @@ struct Tables {
     // A plan holds C >= 1 independent problems (C > 1: batched small problems, e.g. many motion-only clips).
     const int *pose_slot;        // [N] index of the pose in ITS problem's reduced system, -1 if fixed
     const int *pose_row;         // [N] row of the pose in the concatenated dx output, -1 if fixed
+    const int *pose_sys;         // [N] position of the pose in ITS problem's reduced system (a fill-reducing order), -1 if fixed
     const int *frame_prob;       // [K] problem of kx frame k
     const long long *prob_hoff;  // [C] double offset of the problem's [H ; b ; diag(A)] block
     const int *prob_npad;        // [C] padded system size of the problem

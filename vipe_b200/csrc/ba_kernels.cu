@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
     double *const hsys = a.hsys + tb.prob_hoff[prob];
     double *const bsys = hsys + (size_t)n * n;
     double *const adiag = bsys + n;
-    const int ai = tb.pose_slot[src];
+    const int ai = tb.pose_sys[src];
 
     double *G = dsm;            // [d][36]
     double *T = G + d * 36;     // [d][36]
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
         RelPose<double> rp;
         relative_pose<double>(a.poses, src, j, rp);
         adjoint_G<double>(rp, G + m * 36);
-        aj[m] = rp.stereo ? -1 : tb.pose_slot[j];
+        aj[m] = rp.stereo ? -1 : tb.pose_sys[j];
     }
     for (int idx = tid; idx < d * kEdgeVals; idx += NT) {
         const int m = idx / kEdgeVals, r = idx - m * kEdgeVals;

@@ -49,7 +49,9 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
                                 double *dinv /*[npad]*/, double *linvT /*[npad/64][4096]*/,
                                 const double *dampdiag /*[npad] or null*/,
                                 const double *Ain /*null, or multicast address of the ranks' [H;b;diag(A)] partials*/,
-                                int epoch, cudaStream_t st, int *launches);
+                                int epoch, const unsigned char *tstruct /*DEV [T][T] tile structure of L, or null = dense*/,
+                                const int *rowmap /*DEV [npad] system unknown -> dx index, or null = identity*/, cudaStream_t st,
+                                int *launches);
 size_t chol_scratch_ints(int npad);
 // zero every problem's [H ; b ; diag(A)] block and put the identity on the padded diagonals
 cudaError_t launch_system_clear(double *sys, size_t total_doubles, const long long *prob_hoff, const int *prob_n,

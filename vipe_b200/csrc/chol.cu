@@ -24,6 +24,7 @@ namespace vba {
 constexpr int TB = kCholBlock;  // 64
 constexpr int LD = TB + 2;      // 66: keeps 16-byte alignment of 4-double groups in the [k][row] layout
 constexpr int CT = 256;         // threads per CTA
+constexpr int kMaxSparseT = 1024;  // largest tile count the per-tile step list (shared memory) holds; beyond it the solve is dense
 
 // ------------------------------------------------------------------------------------------------
 __global__ void pad_identity_kernel(double *sys, const long long *prob_hoff, const int *prob_n, const int *prob_npad) {
@@ -106,6 +107,11 @@ struct CholArgs {
     // inside the NVSwitch, tile by tile, as the dataflow reaches it -- the all-reduce of the reduced camera system is
     // fused into the Cholesky's own loads.  Outputs (L, y, x) still go to the local H / b.
     const double *Ain;
+    // Sparsity, optional: ts[i * T + j] != 0 when tile (i, j) of L can be non-zero (tile-level symbolic factorisation done by
+    // the plan on a fill-reducing pose order); zero tiles are never claimed, read or waited for.  rowmap: system unknown ->
+    // index in dx (undoes that order).
+    const unsigned char *ts;
+    const int *rowmap;
 };
 
 // one element of the rank-summed input system through the switch (NVLS in-switch reduction)
@@ -536,7 +542,8 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
     double *tmpw = linv8 + 8 * 96;  // [8][160]
     double *As2 = tmpw + 8 * 160;   // second tile pair of the double-buffered k-loop (MINB == 1 only)
     double *Bs2 = As2 + TB * RS;
-    __shared__ int sh_tile, sh_ok, sh_ready;
+    __shared__ int sh_tile, sh_ok, sh_ready, sh_nk;
+    __shared__ unsigned short klist[kMaxSparseT];
     const int T = a.T, ld = a.ld, tid = threadIdx.x;
     const int total = T * (T + 1) / 2 + T;  // lower tiles + one rhs tile per column
     for (;;) {
@@ -561,13 +568,33 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
         }
         const int i = j + (t - (j * (T + 1) - j * (j - 1) / 2));
         const int j0 = j * TB;
+        const unsigned char *ts = a.ts;
+        if (ts && i < T && !ts[(size_t)i * T + j]) continue;  // structurally zero tile: nothing to do, nobody waits for it
         TRACE(t, 0);
+        // the update steps of this tile: k < j with L_ik and L_jk both structurally non-zero, ascending (dense: all of them)
+        if (ts) {
+            if (tid < 32) {
+                int cnt = 0;
+                for (int k0 = 0; k0 < j; k0 += 32) {
+                    const int k = k0 + tid;
+                    const bool need = k < j && (i == T || ts[(size_t)i * T + k]) && ts[(size_t)j * T + k];
+                    const unsigned m = __ballot_sync(0xffffffffu, need);
+                    if (need) klist[cnt + __popc(m & ((1u << tid) - 1u))] = (unsigned short)k;
+                    cnt += __popc(m);
+                }
+                if (tid == 0) sh_nk = cnt;
+            }
+            __syncthreads();
+        }
+        const int nk = ts ? sh_nk : j;
+        auto kof = [&](int idx) -> int { return ts ? (int)klist[idx] : idx; };
 
         if (i == T) {
             // ---- right-hand side tile: y_j = L_jj^-1 (b_j - sum_k L_jk y_k)
             double part = 0.0;
             const int c = tid & 63, q = tid >> 6;  // 4 threads per entry, each takes 16 of the 64 k's
-            for (int k = 0; k < j; k++) {
+            for (int idx = 0; idx < nk; idx++) {
+                const int k = kof(idx);
                 wait_flag(a.flags + (size_t)T * T + k, a.epoch);
                 wait_flag(a.flags + (size_t)j * T + k, a.epoch);
                 const double *Lrow = a.H + (size_t)(j0 + c) * ld + k * TB + q * 16;
@@ -643,16 +670,18 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
             // Software-pipelined part of the k-loop (all steps but the diagonal tile's fused last one): the ready flags of
             // up to 32 steps are polled in one round trip by warp 0, and the tiles of step k+1 are copied asynchronously
             // into the second buffer pair while the tensor cores work on step k.
-            const int kend = (i == j) ? j - 1 : j;
+            // (in list positions: the diagonal tile's step k = j - 1, if it exists, is the fused last one below)
+            const int kend = (i == j && nk > 0 && kof(nk - 1) == j - 1) ? nk - 1 : nk;
             const int lane = tid & 31, warp = tid >> 5;
-            int ready = 0;  // steps k < ready have both of their tiles published
+            int ready = 0;  // steps at list positions < ready have both of their tiles published
             auto ensure = [&](int k) {
                 if (k < ready) return;
                 if (warp == 0) {
                     int r = ready;
                     for (;;) {
-                        const int kk = r + lane;
-                        bool ok = kk < kend;
+                        const int kp = r + lane;
+                        bool ok = kp < kend;
+                        const int kk = ok ? kof(kp) : 0;
                         if (ok) ok = ld_acquire(a.flags + (size_t)i * T + kk) == a.epoch;
                         if (ok && i != j) ok = ld_acquire(a.flags + (size_t)j * T + kk) == a.epoch;
                         const unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -665,8 +694,9 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
                 __syncthreads();
                 ready = sh_ready;
             };
-            auto issue = [&](int k) {
-                double *Ad = (k & 1) ? As2 : As, *Bd = (k & 1) ? Bs2 : Bs;
+            auto issue = [&](int kp) {
+                const int k = kof(kp);
+                double *Ad = (kp & 1) ? As2 : As, *Bd = (kp & 1) ? Bs2 : Bs;
                 tile_cp_async(Ad, a.H + (size_t)i0 * ld + k * TB, ld);
                 if (i != j) tile_cp_async(Bd, a.H + (size_t)j0 * ld + k * TB, ld);
             };
@@ -697,7 +727,8 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
             cp_async_wait<0>();
             kstart = kend > 0 ? kend : 0;
         }
-        for (int k = kstart; k < j; k++) {
+        for (int kp = kstart; kp < nk; kp++) {
+            const int k = kof(kp);
             if (MINB == 1 && i == j && k == j - 1) {
                 // Critical path: the diagonal tile's last update needs L_{j,j-1}.  Instead of waiting for the CTA that
                 // owns that tile to solve and publish it (one more trip through L2), take its pre-solve copy -- ready
@@ -814,6 +845,7 @@ __global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
         const double yj = (tid < TB) ? __ldcg(a.b + j0 + tid) : 0.0;  // y_j (from the factor kernel), fetched off the x chain
         double s = 0.0;
         for (int i = T - 1; i > j; i--) {
+            if (a.ts && !a.ts[(size_t)i * T + j]) continue;  // L_ij is structurally zero
             // stage L_ij while x_i may still be in flight
             double2 v[TB * TB / 2 / CT];
 #pragma unroll
@@ -860,7 +892,7 @@ __global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
             if (bits == 0ull) bits = 0x8000000000000000ull;
             asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(a.xs + j0 + tid), "l"(bits) : "memory");
             a.b[j0 + tid] = x;
-            if (j0 + tid < a.n) a.dx[j0 + tid] = failed ? 0.0f : (float)x;
+            if (j0 + tid < a.n) a.dx[a.rowmap ? a.rowmap[j0 + tid] : j0 + tid] = failed ? 0.0f : (float)x;
         }
     }
 }
@@ -1061,7 +1093,7 @@ cudaError_t launch_small_solve_batch(double *sys, const long long *prob_hoff, co
 
 cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx, int *scratch,
                                 double *dinv, double *linvT, const double *dampdiag, const double *Ain, int epoch,
-                                cudaStream_t st, int *launches) {
+                                const unsigned char *tstruct, const int *rowmap, cudaStream_t st, int *launches) {
     // scratch (ints): [0..1] counters, [2] fail, [16 .. 16+T) unused, [16+T .. 16+2T) preflags, (T+1)*T tile flags, then
     // (16-byte aligned) npad 64-bit words for the backward substitution's x exchange and T * (64*64 + 64) words for the
     // diagonal tiles' fast copies; all zeroed by the memset below
@@ -1095,6 +1127,8 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     a.dampdiag = dampdiag;
     a.linvT = linvT;
     a.Ain = Ain;
+    a.ts = (T <= kMaxSparseT) ? tstruct : nullptr;
+    a.rowmap = rowmap;
     // MINB = 1 double-buffers the tiles of its k-loop (4 tile buffers); MINB = 2 keeps two so that two CTAs fit an SM
     const size_t sm = (size_t)(4 * TB * RS + 2 * TB + 8 * 96 + 8 * 160) * sizeof(double);
     const size_t sm2 = (size_t)(2 * TB * RS + 2 * TB + 8 * 96 + 8 * 160) * sizeof(double);

@@ -126,6 +126,18 @@ class BAPlan:
             self._ws[key] = ws
         return ws
 
+    @property
+    def sys_order(self) -> torch.Tensor:
+        """Position of each free pose in the reduced camera system (a fill-reducing elimination order), [P] int64."""
+        out = torch.empty(self.P, dtype=torch.int64)
+        _lib.check(_lib.lib().vipe_ba_plan_copy_sys_order(self._h, out.data_ptr()), "copy_sys_order")
+        return out
+
+    def system_index(self) -> torch.Tensor:
+        """[6P] int64: index in the system buffer of unknown (pose p, component r) in pose order."""
+        o = self.sys_order
+        return (6 * o[:, None] + torch.arange(6)[None, :]).reshape(-1)
+
     def system_view(self, ws: torch.Tensor) -> torch.Tensor:
         """fp64 view [npad*npad + 2*npad] of the reduced camera system ([H ; b ; diag of the pose Hessian]) inside the workspace (all-reduce target)."""
         n, cnt = C.c_int64(), C.c_int64()

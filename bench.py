@@ -138,10 +138,13 @@ def run_reference(args, pr):
     """--impl reference: the reference's own slam_ext.ba (CUDA kernels + its host Schur/solve code, compiled
     unmodified from /root/reference with oracle/eigen_stub standing in for Eigen) on the same config; if that build
     is absent, the torch CPU port of the same algorithm."""
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference's host code (Schur assembly, the LLT stand-in) is
+    # OpenMP code and is given every core of the box, as when it is run directly
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from oracle import build_ref
 
     cfg = pr.cfg
-    sample_iters = min(cfg.iters, 2)
+    sample_iters = cfg.iters  # the same GN iterations per call as this repo's arm
     mod = build_ref.load() if torch.cuda.is_available() else None
     HW = cfg.ht * cfg.wd
     E = pr.ii.numel()
@@ -154,17 +157,38 @@ def run_reference(args, pr):
             a[11] = sample_iters
             mod.slam_ext.ba(*a)
 
-        for _ in range(args.warmup):
+        import ctypes
+
+        llt_clock = None
+        try:
+            llt_clock = ctypes.CDLL(str(build_ref.so_path())).vipe_eigen_stub_llt_seconds
+            llt_clock.restype = ctypes.c_double
+            llt_clock.argtypes = [ctypes.c_int]
+        except Exception:
+            llt_clock = None
+        steps = max(1, min(args.steps, 20))
+        for _ in range(min(args.warmup, 2)):
             step()
         torch.cuda.synchronize()
+        if llt_clock:
+            llt_clock(1)
         t = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t
+        llt_s = llt_clock(0) if llt_clock else None
+        args.steps = steps
         kind, cores = "reference", os.cpu_count()
-        sample = (f"{cfg.name}: {args.steps} ba calls of {sample_iters} GN iterations each (full problem), reference CUDA kernels on "
-                  f"one B200 + reference host Schur/solve code on the host cores (dense-LLT Eigen stand-in), wall clock")
+        sample = (f"{cfg.name}: {steps} ba calls of {sample_iters} GN iterations each (full problem), reference CUDA kernels on "
+                  f"one B200 + reference host Schur/solve code on {cores} host threads (dense-LLT Eigen stand-in), wall clock")
+        breakdown = None
+        if llt_s is not None:
+            per_it = dt / (steps * sample_iters)
+            breakdown = {"seconds_per_iteration": per_it, "stand_in_llt_seconds_per_iteration": llt_s / (steps * sample_iters),
+                         "stand_in_llt_share": llt_s / dt,
+                         "note": "the LLT stand-in (oracle/eigen_stub, dense, OpenMP) is NOT reference code: Eigen's SimplicialLLT is "
+                                 "absent from the image; the rest of the time is the reference's own CUDA kernels and host code"}
     else:
         from oracle import ba_oracle
 
@@ -183,6 +207,7 @@ def run_reference(args, pr):
         dt = time.perf_counter() - t
         args.steps = steps
         kind, cores = "port", torch.get_num_threads()
+        breakdown = None
         sample = f"{cfg.name}: {steps} ba calls of {sample_iters} GN iterations each, fp32 torch CPU port of ba_cuda"
     value = args.steps * sample_iters / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -193,6 +218,8 @@ def run_reference(args, pr):
                        "gn_iterations_per_step": sample_iters, "lm": cfg.lm, "ep": cfg.ep, "motion_only": cfg.motion_only},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if breakdown:
+        line["reference_breakdown"] = breakdown
     print(json.dumps(line), flush=True)
 
 
@@ -223,6 +250,100 @@ def side_measurement(name, dev, calls=20):
             "edge_pixels_per_sec": pr.edge_pixels * pr.cfg.iters / ms * 1e3}
 
 
+def side_c4(dev, rank, world, collective, steps=3):
+    """C4 (1000 keyframes, 12000 edges, 64x112, 8 GN iterations) beside the headline: one GPU through slam_ext.ba, N GPUs
+    keyframe-sharded with owner-only inputs.  Device-timed, inputs resident, max over ranks."""
+    import torch.distributed as dist
+
+    from vipe_b200.distributed import ba_sharded
+    from vipe_b200.ext import slam_ext
+    from vipe_b200.plan import cached_plan
+    from vipe_b200.synthetic import make_problem
+
+    pr = make_problem("c4")
+    cfg = pr.cfg
+    a = pr.args(dev)
+    kw = {}
+    if world > 1:
+        plan = cached_plan(pr.ii.contiguous(), pr.jj.contiguous(), cfg.n_frames, cfg.ht, cfg.wd, pr.t0, pr.t1, rank, world)
+        own = plan.owned_edges()
+        a[4], a[5] = pr.targets[own].contiguous().to(dev), pr.weights[own].contiguous().to(dev)
+        prof = {"events": []}
+        kw = dict(plan=plan, owned_inputs=True, collective=collective, profile=prof)
+    p0, d0 = a[0].clone(), a[1].clone()
+
+    def run():
+        a[0].copy_(p0)
+        a[1].copy_(d0)
+        if world > 1:
+            ba_sharded(*a, **kw)
+        else:
+            slam_ext.ba(*a)
+
+    for _ in range(2):
+        run()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = 0.0
+    for _ in range(steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a[0].copy_(p0)
+        a[1].copy_(d0)
+        e0.record()
+        if world > 1:
+            ba_sharded(*a, **kw)
+        else:
+            slam_ext.ba(*a)
+        e1.record()
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    out = {"workload": workload_name(cfg), "n_gpus": world, "ms_per_call": ms / steps,
+           "gn_iterations_per_sec": cfg.iters * steps / ms * 1e3, "edge_pixels_per_sec": pr.edge_pixels * cfg.iters * steps / ms * 1e3,
+           "steps": steps}
+    if world > 1:
+        evs = prof["events"][-steps * cfg.iters:]
+        st = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) / len(evs) for i in range(3)]
+        out["stage_ms_per_iteration"] = {"linearize_schur_assemble": st[0], "reduce": st[1], "solve_backsub_retract": st[2]}
+        out["collective"] = prof.get("collective")
+    return out
+
+
+def side_c5(dev, calls=10):
+    """C5: motion-only BA of 64 independent clips (16 keyframes, 120 edges each), one batched call (slam_ext.ba_batch)."""
+    from vipe_b200.ext import slam_ext
+    from vipe_b200.synthetic import CONFIGS, make_problem
+
+    cfg = CONFIGS["c5"]
+    problems = [make_problem(cfg, clip=c) for c in range(cfg.clips)]
+    pr, N, nc = problems[0], cfg.n_frames, cfg.clips
+    cat = lambda xs: torch.cat(xs, dim=0).to(dev)
+    a = [cat([p.poses for p in problems]), cat([p.disps for p in problems]), pr.intrinsics.to(dev),
+         cat([p.disps_sens for p in problems]), cat([p.targets for p in problems]), cat([p.weights for p in problems]),
+         cat([p.eta for p in problems]), cat([p.ii + c * N for c, p in enumerate(problems)]),
+         cat([p.jj + c * N for c, p in enumerate(problems)]), [c * N for c in range(nc + 1)], [c * N + pr.t0 for c in range(nc)],
+         [c * N + pr.t1 for c in range(nc)], cfg.iters, cfg.lm, cfg.ep, cfg.motion_only]
+    p0 = a[0].clone()
+    for _ in range(3):
+        a[0].copy_(p0)
+        slam_ext.ba_batch(*a)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(calls):
+        a[0].copy_(p0)
+        slam_ext.ba_batch(*a)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / calls
+    return {"workload": workload_name(cfg), "ms_per_call": ms, "gn_iterations_per_sec": cfg.iters * nc / ms * 1e3,
+            "edge_pixels_per_sec": pr.edge_pixels * nc * cfg.iters / ms * 1e3, "how": "64 clips in one batched plan, inputs resident"}
+
+
 def workload_name(cfg):
     names = {"c1": "C1 synthetic dense BA: 8 keyframes, 24 edges, 48x64, 2 GN iters",
              "c2": "C2 frontend local BA window: 16 keyframes, 120 edges, 48x64, 4 GN iters",
@@ -240,7 +361,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--collective", default="auto", choices=["auto", "nvls", "allreduce"],
+    ap.add_argument("--no-side", action="store_true", help="skip the C4 / C5 / C2 side measurements")
+    ap.add_argument("--collective", default="auto", choices=["auto", "nvls", "nvls2", "allreduce"],
                     help="N > 1: how the ranks' partial reduced systems are summed (vipe_b200/distributed.py)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -299,6 +421,15 @@ def main():
         dev_args = [batch_args]
     else:
         dev_args = [p.args(dev) for p in problems]
+    shard_plan, own_rows = None, None
+    if sharded:
+        # every rank HOLDS only the targets/weights rows of its own edges, in the plan's CSR order
+        from vipe_b200.plan import cached_plan
+
+        shard_plan = cached_plan(pr.ii.contiguous(), pr.jj.contiguous(), N, cfg.ht, cfg.wd, pr.t0, pr.t1, rank, world)
+        own_rows = shard_plan.owned_edges()
+        dev_args[0][4] = pr.targets[own_rows].contiguous().to(dev)
+        dev_args[0][5] = pr.weights[own_rows].contiguous().to(dev)
     init_state = [(a[0].clone(), a[1].clone()) for a in dev_args]
     plans = [slam_ext.ba_plan(p.ii, p.jj, N, cfg.ht, cfg.wd, p.t0, p.t1) for p in problems] if not (sharded or batched) else []
     K = int(torch.unique(torch.cat([torch.arange(pr.t0, pr.t1), pr.ii])).numel())
@@ -315,7 +446,7 @@ def main():
     def step():
         for a in dev_args:
             if sharded:
-                ba_sharded(*a, exchange=True, profile=shard_prof, collective=args.collective)
+                ba_sharded(*a, exchange=True, profile=shard_prof, collective=args.collective, plan=shard_plan, owned_inputs=True)
             elif batched:
                 slam_ext.ba_batch(*a)
             else:
@@ -420,15 +551,17 @@ def main():
         roofline = {"bound": "hbm", "kernel": "vba::linearize2_kernel on rank 0's shard (linearise+Schur+assemble stage)",
                     "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "algorithmic_bytes_per_launch": own_bytes, "avg_launch_ms": lin_ms,
-                    "collective": ("none: the Cholesky kernel sums the ranks' partial systems through the NVSwitch (multimem.ld_reduce); "
-                                   "'all_reduce' below is the cross-rank barrier" if shard_prof.get("collective") == "nvls"
-                                   else "NCCL all_reduce of the reduced camera system"),
+                    "collective": {"nvls": "none: the Cholesky kernel sums the ranks' partial systems through the NVSwitch (multimem.ld_reduce); "
+                                           "'all_reduce' below is the cross-rank barrier",
+                                   "nvls2": "in-switch reduce-scatter + multicast kernel (multimem.ld_reduce / multimem.st) between two "
+                                            "cross-rank barriers ('all_reduce' below), then a local solve",
+                                   }.get(shard_prof.get("collective"), "NCCL all_reduce of the reduced camera system"),
                     "stage_ms_per_iteration": {"linearize_schur_assemble": shard_stage[0], "all_reduce": shard_stage[1],
                                                "solve_backsub_retract": shard_stage[2]}}
     elif stage_iters > 0:
-        lin_ms = stage_ms[0] / stage_iters  # average duration of one linearise launch (incl. the system clear)
+        lin_ms = stage_ms[0] / stage_iters  # average duration of one linearise launch (events around the kernel, after the system clear)
         achieved = lin_bytes / (lin_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "vba::linearize_kernel (per-source-frame Jacobian/Hessian + Schur Gram)",
+        roofline = {"bound": "hbm", "kernel": "vba::linearize2_kernel<256,false> (per-source-frame Jacobian/Hessian + Schur Gram; the system clear is not in avg_launch_ms)",
                     "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "algorithmic_bytes_per_launch": lin_bytes, "avg_launch_ms": lin_ms,
                     "stage_ms_per_iteration": {"linearize_schur": stage_ms[0] / stage_iters, "assemble": stage_ms[1] / stage_iters,
@@ -442,7 +575,7 @@ def main():
         if jac_ms:
             _, jac_bytes = algorithmic_bytes(cfg, E, K, N, HW, True)
             roofline["jacobian_stage_alone"] = {
-                "kernel": "vba::linearize2_kernel<.., MOTION> (stages 1-2 only: projective transform, J_j, per-edge H/v; no Schur Gram)",
+                "kernel": "vba::lin3_motion_kernel (stages 1-2 only: projective transform, J_j, per-edge H/v; TMA-fed, no Schur Gram)",
                 "avg_launch_ms": jac_ms, "algorithmic_bytes_per_launch": jac_bytes,
                 "achieved": jac_bytes / (jac_ms * 1e-3) / 1e9, "unit": "GB/s", "frac": jac_bytes / (jac_ms * 1e-3) / 1e9 / peak}
         prof = ROOT / "profiles" / "traffic.json"
@@ -455,6 +588,10 @@ def main():
     # end-to-end through the public API with host buffers (rank-local inputs in pinned memory)
     if batched:
         host_args = [[x.cpu().pin_memory() if torch.is_tensor(x) else x for x in batch_args]]
+    elif sharded:
+        h = pr.args()
+        h[4], h[5] = pr.targets[own_rows].contiguous(), pr.weights[own_rows].contiguous()  # this rank uploads its own edges only
+        host_args = [[x.pin_memory() if torch.is_tensor(x) else x for x in h]]
     else:
         host_args = [[x.pin_memory() if torch.is_tensor(x) else x for x in p.args()] for p in problems]
     h2d = sum(x.numel() * x.element_size() for h in host_args for x in h if torch.is_tensor(x))
@@ -467,10 +604,7 @@ def main():
 
     feed = HostFeed(dev)
     if sharded:
-        from vipe_b200.plan import cached_plan
-
-        shard_plan = cached_plan(pr.ii.contiguous(), pr.jj.contiguous(), N, cfg.ht, cfg.wd, pr.t0, pr.t1, rank, world)
-        e2e_fn = lambda *a: ba_sharded(*a, exchange=True, collective=args.collective, plan=shard_plan)
+        e2e_fn = lambda *a: ba_sharded(*a, exchange=True, collective=args.collective, plan=shard_plan, owned_inputs=True)
     elif batched:
         e2e_fn = slam_ext.ba_batch
     else:
@@ -504,6 +638,33 @@ def main():
     # lasts ~0.1 s, one or two nvidia-smi samples)
     clocks = sampler.stop()
 
+    # the sharded result against a single-GPU run of the same operator on rank 0 (the only place the driver sees it)
+    sharded_parity = None
+    if sharded:
+        from vipe_b200.synthetic import disp_error, pose_errors
+
+        reset()
+        step()
+        barrier()
+        if rank == 0:
+            full = pr.args(dev)
+            slam_ext.ba(*full)
+            torch.cuda.synchronize()
+            te, re_ = pose_errors(dev_args[0][0], full[0], pr.t0, pr.t1)
+            kxs = torch.unique(torch.cat([torch.arange(pr.t0, pr.t1), pr.ii]))
+            sharded_parity = {"vs": "slam_ext.ba on one GPU, same inputs, same iterations", "translation_rel": te, "rotation_max_rad": re_,
+                              "disparity_rel": disp_error(dev_args[0][1], full[1], kxs),
+                              "bounds": {"translation_rel": 1e-4, "rotation_max_rad": 1e-4, "disparity_rel": 1e-3}}
+            del full
+        barrier()
+    side = {}
+    if not args.no_side and args.workload == "c3":
+        del dev_args, init_state, host_args, out_host, feed
+        torch.cuda.empty_cache()
+        side["c4"] = side_c4(dev, rank, world, args.collective)
+        if world == 1:
+            side["c5"] = side_c5(dev)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if clips == 1 else "weak",
@@ -511,7 +672,7 @@ def main():
                 "edge_pixels_per_sec": value * edge_px,
                 "config": {"workload": workload_name(cfg), "frames": N, "edges": E, "ht": cfg.ht, "wd": cfg.wd,
                            "gn_iterations_per_step": cfg.iters, "lm": cfg.lm, "ep": cfg.ep, "motion_only": cfg.motion_only,
-                           "clips": clips, "parallelism": (f"keyframe-sharded x{world}, " + ("in-switch reduction fused into the solve (NVLS)" if shard_prof.get("collective") == "nvls" else "NCCL all-reduce per iteration")) if sharded else ("clips batched per rank, no collective" if clips > 1 else "single"),
+                           "clips": clips, "parallelism": (f"keyframe-sharded x{world}, " + {"nvls": "in-switch reduction fused into the solve (NVLS)", "nvls2": "in-switch reduce-scatter + multicast (NVLS), local solve"}.get(shard_prof.get("collective"), "NCCL all-reduce per iteration") + ", owner-only targets/weights") if sharded else ("clips batched per rank, no collective" if clips > 1 else "single"),
                            "l2": "flushed between timed steps (256 MB write)", "timing": "cuda events per step, max over ranks",
                            "wall_s_timed_region": wall},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -519,7 +680,11 @@ def main():
                         "how": "slam_ext.ba fed from pinned host buffers by vipe_b200.host_feed.HostFeed: every step's H2D (copy stream, "
                                "overlapping the previous step's solve) and D2H of poses+disps are inside the timed region"},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
-        if world == 1 and args.workload != "c2":
+        if sharded_parity is not None:
+            line["sharded_parity"] = sharded_parity
+        for k2, v2 in side.items():
+            line[k2] = v2
+        if world == 1 and args.workload != "c2" and not args.no_side:
             line["frontend_c2"] = side_measurement("c2", dev)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(pr)

@@ -163,6 +163,25 @@ int vipe_ba_solve_update(const vipe_ba_plan *plan, const vipe_ba_tensors *t, voi
  * finished reading buffer k, which the barrier of iteration k+1 guarantees).  Needs 6*(t1-t0) > 128.  NULL, NULL: off.
  */
 int vipe_ba_set_peer_system(vipe_ba_plan *plan, double *accum_local, const double *accum_multicast);
+/*
+ * The same reduction in two steps (better from 4 GPUs on: the factorisation then reads local memory at full speed):
+ * with vipe_ba_set_peer_system(plan, accum_local, accum_multicast) still routing the accumulation, call
+ * vipe_ba_peer_reduce between two cross-rank barriers -- every rank sums 1/world of the tiles over all instances of `accum`
+ * (multimem.ld_reduce) and multicasts them into all instances of `reduced` (multimem.st) -- and point the solve at this
+ * rank's instance of `reduced` with vipe_ba_set_solve_buffer (the solve factorises it in place; NULL: back to the
+ * workspace / the fused loads).  One accumulation buffer suffices in this mode.
+ */
+int vipe_ba_peer_reduce(const vipe_ba_plan *plan, const double *accum_multicast, double *reduced_multicast, int rank, int world,
+                        void *stream);
+int vipe_ba_set_solve_buffer(vipe_ba_plan *plan, double *reduced_local);
+/*
+ * Owner-only pixel inputs for sharded plans (a rank HOLDS the targets/weights of its edges): when
+ * on, `targets` / `weights` in vipe_ba_tensors are [n_owned, 2, ht, wd], the rows of this rank's edges in the order of
+ * vipe_ba_plan_copy_owned_edges (the plan's CSR order over the owned source frames).  Everything else stays replicated.
+ */
+int vipe_ba_set_owned_rows(vipe_ba_plan *plan, int on);
+int64_t vipe_ba_plan_num_owned_edges(const vipe_ba_plan *plan);
+int vipe_ba_plan_copy_owned_edges(const vipe_ba_plan *plan, int64_t *edge_ids_out);
 
 /* DEV fp64 buffer holding [H (n x n, row-major, lower triangle valid) ; b (n) ; diag of the pose Hessian (n)],
    n = 6*(t1-t0) rounded up to 64; count_out = n*n + 2n.  This is what a sharded run all-reduces. */

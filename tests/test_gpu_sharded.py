@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, name, out, collective):
+def _worker(rank, world, port, name, out, collective, owned=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dev = torch.device("cuda", rank)
@@ -24,7 +24,16 @@ def _worker(rank, world, port, name, out, collective):
     pr = make_problem(name)
     a = pr.args(dev)
     prof = {}
-    dx, dz = ba_sharded(*a, collective=collective, profile=prof)
+    kw = {}
+    if owned:  # this rank holds only the targets/weights rows of its own edges
+        from vipe_b200.ext import slam_ext
+
+        cfg = pr.cfg
+        plan = slam_ext.ba_plan(pr.ii, pr.jj, cfg.n_frames, cfg.ht, cfg.wd, pr.t0, pr.t1, rank, world)
+        own = plan.owned_edges()
+        a[4], a[5] = pr.targets[own].contiguous().to(dev), pr.weights[own].contiguous().to(dev)
+        kw = dict(plan=plan, owned_inputs=True)
+    dx, dz = ba_sharded(*a, collective=collective, profile=prof, **kw)
     assert prof["collective"] == collective
     torch.cuda.synchronize()
     if rank == 0:
@@ -42,10 +51,12 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("name,collective", [("c2", "allreduce"), ("c3", "allreduce"), ("c3", "nvls")])
-def test_sharded_matches_single_gpu(lib_built, tmp_path, name, collective):
+@pytest.mark.parametrize("name,collective,owned", [("c2", "allreduce", False), ("c3", "allreduce", True), ("c3", "nvls", False),
+                                                   ("c3", "nvls2", True)])
+def test_sharded_matches_single_gpu(lib_built, tmp_path, name, collective, owned):
     """"nvls": no all-reduce launch; the Cholesky kernel reads the sum of the ranks' partial systems through the NVSwitch
-    (multimem.ld_reduce), see vipe_b200/distributed.py PeerSystem."""
+    (multimem.ld_reduce), see vipe_b200/distributed.py PeerSystem.  "nvls2": the in-switch sum as a reduce-scatter +
+    multicast kernel of its own, then a local solve.  `owned`: every rank is given only its own edges' targets/weights."""
     world = torch.cuda.device_count()
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -54,7 +65,7 @@ def test_sharded_matches_single_gpu(lib_built, tmp_path, name, collective):
     from vipe_b200.synthetic import disp_error, make_problem, pose_errors
 
     out = tmp_path / "r0.pt"
-    mp.spawn(_worker, args=(world, _free_port(), name, str(out), collective), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), name, str(out), collective, owned), nprocs=world, join=True)
     got = torch.load(out)
     pr = make_problem(name)
     a = pr.args(torch.device("cuda:0"))

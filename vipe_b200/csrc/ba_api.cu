@@ -1,6 +1,7 @@
 // C ABI of libvipe_ba.so (include/vipe_ba.h): plan construction (index bookkeeping on the host, once per
 // graph), workspace layout, and the stream-ordered Gauss-Newton loop.  No torch, no allocation, no sync.
 #include <algorithm>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -82,6 +83,7 @@ struct vipe_ba_plan {
     // workspace layout (byte offsets)
     size_t off_kx = 0, off_fptr = 0, off_fedge = 0, off_ejj = 0, off_gbase = 0, off_mbase = 0, idx_bytes = 0;
     size_t off_epart = 0, off_gpart = 0, off_msc = 0, off_q = 0, off_qw = 0, off_sys = 0, off_dx = 0, off_flag = 0;
+    size_t off_gdx = 0, off_gdz = 0;
     size_t total = 0, flag_bytes = 0;
     mutable int epoch = 0;
     std::vector<unsigned char> blob;  // host image of the index tables
@@ -103,6 +105,8 @@ struct vipe_ba_plan {
     // multi-GPU fused reduction (vipe_ba_set_peer_system): where this rank accumulates its partial system, and the
     // multicast address through which the solve reads the sum over ranks
     mutable double *peer_accum = nullptr;
+    mutable double *solve_buf = nullptr;  // where solve_update reads and factorises the system (null: the workspace)
+    mutable int rows_by_slot = 0;         // targets/weights hold only this rank's edges, in CSR slot order
     mutable const double *peer_mc = nullptr;
     // optional stage timing
     bool profile = false;
@@ -459,6 +463,8 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     p->off_qw = take(sizeof(float) * (size_t)K * p->HW);
     p->off_sys = take(sizeof(double) * p->sys_doubles);  // per problem [H ; b ; diag(A)]
     p->off_dx = take(sizeof(double) * ((size_t)p->npad + (size_t)p->npad * kCholBlock));  // 1/diag(L), then L_jj^-T tiles
+    p->off_gdx = take(sizeof(float) * ((size_t)6 * std::max(P, 1) + 1));  // graph-owned dx / dz (see vipe_ba_run)
+    p->off_gdz = take(sizeof(float) * (size_t)std::max(K, 1) * p->HW);
     p->off_flag = take(sizeof(int) * chol_scratch_ints(p->npad));
     p->flag_bytes = sizeof(int) * chol_scratch_ints(p->npad);
     p->total = off;
@@ -580,6 +586,8 @@ static Tables make_tables(const vipe_ba_plan *p, void *ws) {
     tb.ntile = p->ntile;
     tb.k_lo = p->k_lo;
     tb.k_hi = p->k_hi;
+    tb.rows_by_slot = p->rows_by_slot;
+    tb.slot_lo = p->fptr[p->k_lo];
     return tb;
 }
 
@@ -596,13 +604,21 @@ static int check_tensors(const vipe_ba_plan *p, const vipe_ba_tensors *t, int mo
     if (!p || !t) return fail("null plan/tensors");
     if (!t->poses || !t->disps || !t->intrinsics || !t->dx_out) return fail("null tensor pointer");
     // a graph without edges has empty targets/weights, whose storage pointer is null
-    if (p->E > 0 && (!t->targets || !t->weights)) return fail("null tensor pointer");
+    const bool no_rows = p->rows_by_slot && p->fptr[p->k_hi] == p->fptr[p->k_lo];  // a shard that owns no edge
+    if (p->E > 0 && !no_rows && (!t->targets || !t->weights)) return fail("null tensor pointer");
     if (!motion_only && (!t->disps_sens || !t->eta || !t->dz_out)) return fail("disps_sens/eta/dz_out required unless motion_only");
+    // the kernels read and write the pixel arrays with 8/16-byte vector accesses and 16-byte bulk copies whenever ht*wd is
+    // even: a misaligned base would be a sticky device fault, so it is refused here (the Python operator re-aligns by copy)
+    if (p->HW % 2 == 0) {
+        const void *px[] = {t->disps, t->disps_sens, t->targets, t->weights, t->eta, t->dz_out};
+        for (const void *q : px)
+            if (q && (reinterpret_cast<uintptr_t>(q) & 15u)) return fail("pixel arrays (disps, disps_sens, targets, weights, eta, dz_out) must be 16-byte aligned");
+    }
     return 0;
 }
 
 static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void *ws, int motion_only, cudaStream_t st,
-                          cudaEvent_t mid) {
+                          cudaEvent_t mid, cudaEvent_t after_clear = nullptr) {
     if (check_tensors(p, t, motion_only)) return 1;
     if (!ws) return fail("null workspace");
     unsigned char *w = (unsigned char *)ws;
@@ -612,6 +628,7 @@ static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void 
         VBA_CUDA(launch_system_clear(H, p->sys_doubles, t0b.prob_hoff, t0b.prob_n, t0b.prob_npad, p->C, p->any_padding, st));
     }
     p->launches += p->any_padding ? 2 : 1;
+    if (after_clear) VBA_CUDA(cudaEventRecord(after_clear, st));  // stage timing starts here: the system clear is not the linearisation
     const int nframes = p->k_hi - p->k_lo;
     if (nframes <= 0 || p->P <= 0) return 0;
 
@@ -706,7 +723,7 @@ static int solve_update_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, vo
     if (!ws) return fail("null workspace");
     if (p->P <= 0) return 0;
     unsigned char *w = (unsigned char *)ws;
-    double *H = (double *)(w + p->off_sys);
+    double *H = p->solve_buf ? p->solve_buf : (double *)(w + p->off_sys);
     double *b = H + (size_t)p->npad * p->npad;
     int *scratch = (int *)(w + p->off_flag);
     int cnt = 0;
@@ -717,11 +734,11 @@ static int solve_update_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, vo
         // the solver adds ep + lm * diag(A) to every diagonal entry; diag(A) is 0 in the focal row (its LM term went in
         // with the assembly), so the focal row ends up with focal_ep
         if (focal) VBA_CUDA(launch_add_scalar(H + (size_t)p->n * p->npad + p->n, (double)p->opt.focal_ep - (double)ep, st));
-        if (p->peer_mc && p->npad <= 2 * kCholBlock)
+        if ((p->peer_mc || p->solve_buf) && p->npad <= 2 * kCholBlock)
             return fail("the fused multi-GPU reduction needs the tiled solver (more than 128 unknowns); use the all-reduce path");
         VBA_CUDA(launch_damped_solve(H, b, p->n + (focal ? 1 : 0), p->npad, lm, ep, t->dx_out, scratch, (double *)(w + p->off_dx),
                                      (double *)(w + p->off_dx) + p->npad, p->opt.damp_on_pose_hessian ? b + p->npad : nullptr,
-                                     p->peer_mc, p->epoch, p->ordered ? (const unsigned char *)(w + p->off_tstruct) : nullptr,
+                                     p->solve_buf ? nullptr : p->peer_mc, p->epoch, p->ordered ? (const unsigned char *)(w + p->off_tstruct) : nullptr,
                                      nullptr, st, &cnt));
     } else {  // many small independent problems: one CTA each
         VBA_CUDA(launch_small_solve_batch(H, tbs.prob_hoff, tbs.prob_n, tbs.prob_npad, tbs.prob_row0, p->C, lm, ep, t->dx_out,
@@ -763,9 +780,8 @@ extern "C" int vipe_ba_solve_update(const vipe_ba_plan *p, const vipe_ba_tensors
 
 static int run_iteration(const vipe_ba_plan *p, const vipe_ba_tensors *t, void *ws, float lm, float ep, int motion_only,
                          cudaStream_t st, cudaEvent_t *ev) {
-    // the system clear is counted with the linearise stage
-    if (ev) VBA_CUDA(cudaEventRecord(ev[0], st));
-    if (linearize_impl(p, t, ws, motion_only, st, ev ? ev[1] : nullptr)) return 1;
+    // stage 0 = the linearisation kernel(s) alone: its start event is recorded after the system clear
+    if (linearize_impl(p, t, ws, motion_only, st, ev ? ev[1] : nullptr, ev ? ev[0] : nullptr)) return 1;
     if (ev) VBA_CUDA(cudaEventRecord(ev[2], st));
     if (solve_update_impl(p, t, ws, lm, ep, motion_only, st, ev ? ev[3] : nullptr)) return 1;
     if (ev) VBA_CUDA(cudaEventRecord(ev[4], st));
@@ -802,7 +818,12 @@ static int run_iteration(const vipe_ba_plan *p, const vipe_ba_tensors *t, void *
 
 static bool same_args(const vipe_ba_plan::GraphEntry &g, const vipe_ba_tensors *t, void *ws, int iterations, float lm,
                       float ep, int motion_only) {
-    return std::memcmp(&g.t, t, sizeof(*t)) == 0 && g.ws == ws && g.iterations == iterations && g.lm == lm && g.ep == ep &&
+    // dx_out / dz_out are NOT part of the key: a captured run writes its updates into the workspace and they are copied out
+    // after the launch, so callers that keep (and therefore re-allocate) their result tensors still replay
+    vipe_ba_tensors a = g.t, b = *t;
+    a.dx_out = b.dx_out = nullptr;
+    a.dz_out = b.dz_out = nullptr;
+    return std::memcmp(&a, &b, sizeof(a)) == 0 && g.ws == ws && g.iterations == iterations && g.lm == lm && g.ep == ep &&
            g.motion_only == motion_only;
 }
 
@@ -816,9 +837,51 @@ extern "C" int vipe_ba_set_peer_system(vipe_ba_plan *p, double *accum_local, con
     return 0;
 }
 
+extern "C" int vipe_ba_set_solve_buffer(vipe_ba_plan *p, double *local) {
+    if (!p) return fail("null plan");
+    if (local && p->C != 1) return fail("batched plans are not sharded");
+    p->solve_buf = local;
+    return 0;
+}
+
+extern "C" int vipe_ba_set_owned_rows(vipe_ba_plan *p, int on) {
+    if (!p) return fail("null plan");
+    p->rows_by_slot = on != 0;
+    for (auto &g : p->graphs)  // captured graphs have the old row addressing baked in
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    p->graphs.clear();
+    return 0;
+}
+
+extern "C" int64_t vipe_ba_plan_num_owned_edges(const vipe_ba_plan *p) { return p ? p->fptr[p->k_hi] - p->fptr[p->k_lo] : -1; }
+extern "C" int vipe_ba_plan_copy_owned_edges(const vipe_ba_plan *p, int64_t *o) {
+    if (!p || !o) return fail("null argument");
+    for (int s2 = p->fptr[p->k_lo]; s2 < p->fptr[p->k_hi]; s2++) o[s2 - p->fptr[p->k_lo]] = p->fedge[s2];
+    return 0;
+}
+
+extern "C" int vipe_ba_peer_reduce(const vipe_ba_plan *p, const double *accum_multicast, double *reduced_multicast, int rank,
+                                   int world, void *stream) {
+    if (!p || !accum_multicast || !reduced_multicast) return fail("null argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail("bad rank/world");
+    VBA_CUDA(launch_peer_reduce(accum_multicast, reduced_multicast, p->npad, rank, world, (cudaStream_t)stream));
+    p->launches++;
+    return 0;
+}
+
 extern "C" int vipe_ba_set_graphs(vipe_ba_plan *p, int on) {
     if (!p) return fail("null plan");
     p->use_graphs = on != 0;
+    return 0;
+}
+
+// a replayed graph leaves the last iteration's updates in the workspace: hand them to the caller's tensors
+static int copy_graph_results(const vipe_ba_plan *p, const vipe_ba_tensors *t, void *ws, int motion_only, cudaStream_t st) {
+    const unsigned char *w = (const unsigned char *)ws;
+    const size_t ndx = (size_t)6 * p->P + (p->opt.optimize_focal ? 1 : 0);
+    VBA_CUDA(cudaMemcpyAsync(t->dx_out, w + p->off_gdx, sizeof(float) * ndx, cudaMemcpyDeviceToDevice, st));
+    if (!motion_only && t->dz_out)
+        VBA_CUDA(cudaMemcpyAsync(t->dz_out, w + p->off_gdz, sizeof(float) * (size_t)p->K * p->HW, cudaMemcpyDeviceToDevice, st));
     return 0;
 }
 
@@ -839,7 +902,7 @@ extern "C" int vipe_ba_run(const vipe_ba_plan *p, const vipe_ba_tensors *t, void
         if (entry && entry->exec) {
             VBA_CUDA(cudaGraphLaunch(entry->exec, st));
             p->launches = entry->launches;
-            return 0;
+            return copy_graph_results(p, t, ws, motion_only, st);
         }
         if (!entry) {
             if (p->graphs.size() >= 8) {
@@ -855,7 +918,10 @@ extern "C" int vipe_ba_run(const vipe_ba_plan *p, const vipe_ba_tensors *t, void
             VBA_CUDA(cudaStreamBeginCapture(p->capture_stream, cudaStreamCaptureModeThreadLocal));
             p->launches = 0;
             int rc = 0;
-            for (int it = 0; it < iterations && !rc; it++) rc = run_iteration(p, t, ws, lm, ep, motion_only, p->capture_stream, nullptr);
+            vipe_ba_tensors tg = *t;  // the graph's own result buffers
+            tg.dx_out = (float *)((unsigned char *)ws + p->off_gdx);
+            tg.dz_out = motion_only ? nullptr : (float *)((unsigned char *)ws + p->off_gdz);
+            for (int it = 0; it < iterations && !rc; it++) rc = run_iteration(p, &tg, ws, lm, ep, motion_only, p->capture_stream, nullptr);
             cudaError_t ce = cudaStreamEndCapture(p->capture_stream, &graph);
             if (rc || ce != cudaSuccess || !graph) {
                 if (graph) cudaGraphDestroy(graph);
@@ -870,7 +936,7 @@ extern "C" int vipe_ba_run(const vipe_ba_plan *p, const vipe_ba_tensors *t, void
                     entry->exec = exec;
                     entry->launches = p->launches;
                     VBA_CUDA(cudaGraphLaunch(exec, st));
-                    return 0;
+                    return copy_graph_results(p, t, ws, motion_only, st);
                 }
                 cudaGetLastError();
                 p->use_graphs = false;

@@ -33,7 +33,12 @@ struct Tables {
     const int *prob_n;           // [C] system size 6 * (free poses)
     const int *prob_row0;        // [C] first dx row of the problem
     int K, E, N, HW, wd, ntile, k_lo, k_hi, C;
+    // owner-only pixel inputs (multi-GPU): targets/weights hold just the rows of this rank's edges, in CSR slot order
+    int rows_by_slot = 0, slot_lo = 0;
 };
+
+// row of edge `e` (CSR slot `slot`) in the targets/weights arrays
+__device__ __forceinline__ int edge_row(const Tables &tb, int slot, int e) { return tb.rows_by_slot ? slot - tb.slot_lo : e; }
 
 // Semantic switches (defaults = the reference's CUDA BA; the other values serve the conventions of vipe/slam's Python BA,
 // SURVEY.md section 8(a')).  Mirrors vipe_ba_options in include/vipe_ba.h.

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(NT) linearize_kernel(const LinArgs a) {
         const int e = tb.fedge[s0 + m];
         RelPose<float> rp;
         relative_pose<float>(a.poses, src, tb.e_jj[e], rp);
-        write_edge_consts(ec + m * kEcStride, rp, e);
+        write_edge_consts(ec + m * kEcStride, rp, edge_row(tb, s0 + m, e));
     }
     const float fx = __ldg(a.intr + 0), fy = __ldg(a.intr + 1), cx = __ldg(a.intr + 2), cy = __ldg(a.intr + 3);
 
@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(NT) backsub_kernel(const BackArgs a) {
         const int j = tb.e_jj[e];
         RelPose<float> rp;
         relative_pose<float>(a.poses, src, j, rp);
-        write_edge_consts(ec + m * kEcStride, rp, e);
+        write_edge_consts(ec + m * kEcStride, rp, edge_row(tb, s0 + m, e));
         float G[36];
         adjoint_G<float>(rp, G);
         const int lo = a.opt.backsub_all_poses ? 0 : 1;  // Q4: the reference skips pose index 0 (of its problem) on purpose
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(kFocalNT) focal_kernel(const FocalArgs a) {
         const int e = tb.fedge[s0 + m];
         RelPose<float> rp;
         relative_pose<float>(a.poses, src, tb.e_jj[e], rp);
-        write_edge_consts(ec + m * kEcStride, rp, e);
+        write_edge_consts(ec + m * kEcStride, rp, edge_row(tb, s0 + m, e));
     }
     for (int idx = tid; idx < d * NW * kFocalStride; idx += kFocalNT) red[idx] = 0.0f;
     const float fx = __ldg(a.intr + 0), fy = __ldg(a.intr + 1), cx = __ldg(a.intr + 2), cy = __ldg(a.intr + 3);

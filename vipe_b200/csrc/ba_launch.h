@@ -53,6 +53,10 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
                                 const int *rowmap /*DEV [npad] system unknown -> dx index, or null = identity*/, cudaStream_t st,
                                 int *launches);
 size_t chol_scratch_ints(int npad);
+// Two-step in-switch all-reduce of the ranks' partial systems [H (lower tiles) ; b ; diag(A)]: this rank sums every world-th
+// tile over all instances (multimem.ld_reduce through `accum_mc`) and multicasts the sums into every rank's instance of
+// `reduced_mc` (multimem.st).  Between two cross-rank barriers.
+cudaError_t launch_peer_reduce(const double *accum_mc, double *reduced_mc, int npad, int rank, int world, cudaStream_t st);
 // zero every problem's [H ; b ; diag(A)] block and put the identity on the padded diagonals
 cudaError_t launch_system_clear(double *sys, size_t total_doubles, const long long *prob_hoff, const int *prob_n,
                                 const int *prob_npad, int n_prob, bool any_padding, cudaStream_t st);

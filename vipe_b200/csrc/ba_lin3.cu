@@ -480,13 +480,13 @@ __global__ void __launch_bounds__(kThreads, 1) lin3_kernel(const LinArgs a, cons
         auto issue_stage = [&](uint32_t sq) {
             if (sq >= nstage) return;
             const Lin3Item &pi = items[blockIdx.x + (size_t)(sq / spi) * gridDim.x];
-            const int e = pi.edge[jw];
-            if (e < 0) return;
+            if (pi.edge[jw] < 0) return;
+            const int erow = edge_row(tb, pi.s0 + jw, pi.edge[jw]);
             const int b = sq & 1;
             if (lane == 0) mbar_arrive_expect_tx(myfull + b, (uint32_t)L::stage_bytes);
             __syncwarp();
             if (lane < 4) {
-                const float *src = (lane < 2 ? a.targets : a.weights) + ((size_t)e * 2 + (lane & 1)) * HW + pi.px0 + (sq % spi) * STAGE_PX;
+                const float *src = (lane < 2 ? a.targets : a.weights) + ((size_t)erow * 2 + (lane & 1)) * HW + pi.px0 + (sq % spi) * STAGE_PX;
                 bulk_g2s(mystage + (size_t)b * L::stage_bytes + (size_t)lane * STAGE_PX * 4, src, STAGE_PX * 4, myfull + b);
             }
         };
@@ -662,12 +662,12 @@ __global__ void __launch_bounds__(32 * kMotionWarps, 1) lin3_motion_kernel(const
         if (sq >= nstage) return;
         const long long u = u0 + (long long)(sq / spi) * wstride;
         const int slot = slot_lo + (int)(u / nchunk), ch = (int)(u % nchunk);
-        const int e = tb.fedge[slot];
+        const int erow = edge_row(tb, slot, tb.fedge[slot]);
         const int b = sq & 1;
         if (lane == 0) mbar_arrive_expect_tx(myfull + b, (uint32_t)stage_bytes);
         __syncwarp();
         if (lane < 4) {
-            const float *src = (lane < 2 ? a.targets : a.weights) + ((size_t)e * 2 + (lane & 1)) * HW + (size_t)ch * nsub * TILE + (sq % spi) * STAGE_PX;
+            const float *src = (lane < 2 ? a.targets : a.weights) + ((size_t)erow * 2 + (lane & 1)) * HW + (size_t)ch * nsub * TILE + (sq % spi) * STAGE_PX;
             bulk_g2s(mystage + (size_t)b * stage_bytes + (size_t)lane * STAGE_PX * 4, src, STAGE_PX * 4, myfull + b);
         }
     };

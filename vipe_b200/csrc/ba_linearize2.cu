@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(2 * NT, (MOTION && NT == 256) ? 2 : 1) lineari
         for (int q = 0; q < 9; q++) c[q] = splat(rp.R[q]);
 #pragma unroll
         for (int q = 0; q < 3; q++) c[9 + q] = splat(rp.t[q]);
-        c[12] = make_float2(rp.stereo ? 1.0f : 0.0f, __int_as_float(e));
+        c[12] = make_float2(rp.stereo ? 1.0f : 0.0f, __int_as_float(edge_row(tb, s0 + m, e)));
     }
     const float fx = __ldg(a.intr + 0), fy = __ldg(a.intr + 1), cx = __ldg(a.intr + 2), cy = __ldg(a.intr + 3);
     const float2 fx2 = splat(fx), fy2 = splat(fy);
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(2 * NT, (MOTION && NT == 256) ? 2 : 1) lineari
     };
     // the first edge's loads leave before the barrier (edge id straight from the table, not from the staged constants):
     // their trip to HBM overlaps the pose prologue of the d threads above
-    if (inb && half < d) issue_loads_e(tb.fedge[s0 + half]);
+    if (inb && half < d) issue_loads_e(edge_row(tb, s0 + half, tb.fedge[s0 + half]));
     // sensor disparity and damping of this pixel pair (used after the edge loop by the even-edge half): fetched now
     float2 ds_pre = make_float2(0.0f, 0.0f), et_pre = make_float2(0.0f, 0.0f);
     if (!MOTION && inb && half == 0) {

@@ -1154,6 +1154,42 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// NVLS all-reduce of the reduced camera system in two steps (reduce-scatter + all-gather through the switch).
+// Work items: the T (T + 1) / 2 lower 64 x 64 tiles, then 2 T pieces of 64 entries of [b ; diag(A)]; item t belongs to rank
+// t mod world.  Every element is read by exactly one rank (its owner) and written by it into all instances of `out`.
+__global__ void __launch_bounds__(256) peer_reduce_kernel(const double *__restrict__ mc_in, double *__restrict__ mc_out, int ld, int T,
+                                                          int rank, int world) {
+    const int ntile = T * (T + 1) / 2, nitem = ntile + 2 * T;
+    for (int item = rank + (int)blockIdx.x * world; item < nitem; item += (int)gridDim.x * world) {
+        if (item < ntile) {
+            int i = (int)((sqrtf(8.0f * (float)item + 1.0f) - 1.0f) * 0.5f);
+            while ((i + 1) * (i + 2) / 2 <= item) i++;
+            while (i * (i + 1) / 2 > item) i--;
+            const int j = item - i * (i + 1) / 2;
+            for (int idx = threadIdx.x; idx < TB * TB; idx += 256) {
+                const size_t off = (size_t)(i * TB + (idx >> 6)) * ld + j * TB + (idx & 63);
+                const double v = mc_load_sum(mc_in + off);
+                asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc_out + off), "d"(v) : "memory");
+            }
+        } else if (threadIdx.x < TB) {
+            const size_t off = (size_t)ld * ld + (size_t)(item - ntile) * TB + threadIdx.x;
+            const double v = mc_load_sum(mc_in + off);
+            asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc_out + off), "d"(v) : "memory");
+        }
+    }
+    __threadfence_system();
+}
+
+cudaError_t launch_peer_reduce(const double *accum_mc, double *reduced_mc, int npad, int rank, int world, cudaStream_t st) {
+    const int T = npad / TB;
+    const int nitem = T * (T + 1) / 2 + 2 * T;
+    int grid = (nitem + world - 1) / world;
+    if (grid > 592) grid = 592;
+    peer_reduce_kernel<<<grid, 256, 0, st>>>(accum_mc, reduced_mc, npad, T, rank, world);
+    return cudaGetLastError();
+}
+
 size_t chol_scratch_ints(int npad) {
     const int T = npad / TB;
     return ((16 + 2 * (size_t)T + (size_t)(T + 1) * T + 3) & ~(size_t)3) + 2 * (size_t)npad + 2 * (size_t)T * (TB * TB + TB);

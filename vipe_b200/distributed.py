@@ -52,7 +52,7 @@ class PeerSystem:
 
             _, npad = plan.system_view(plan.workspace(dev))
             count = npad * npad + 2 * npad
-            self.bufs = [symm.empty(count, dtype=torch.float64, device=dev) for _ in range(2)]
+            self.bufs = [symm.empty(count, dtype=torch.float64, device=dev) for _ in range(3)]  # two accumulators + the reduced system
             for b in self.bufs:
                 b.zero_()
             good = True
@@ -107,6 +107,16 @@ class CudaShardEngine:
     def use_peer_buffer(self, local_ptr, multicast_ptr):
         _lib.check(_lib.lib().vipe_ba_set_peer_system(self.plan.handle, local_ptr, multicast_ptr), "vipe_ba_set_peer_system")
 
+    def use_solve_buffer(self, local_ptr):
+        _lib.check(_lib.lib().vipe_ba_set_solve_buffer(self.plan.handle, local_ptr), "vipe_ba_set_solve_buffer")
+
+    def use_owned_rows(self, on: bool):
+        _lib.check(_lib.lib().vipe_ba_set_owned_rows(self.plan.handle, int(on)), "vipe_ba_set_owned_rows")
+
+    def peer_reduce(self, accum_mc, reduced_mc, rank, world):
+        _lib.check(_lib.lib().vipe_ba_peer_reduce(self.plan.handle, accum_mc, reduced_mc, int(rank), int(world), self._stream()),
+                   "vipe_ba_peer_reduce")
+
     def solve_update(self, lm: float, ep: float):
         _lib.check(_lib.lib().vipe_ba_solve_update(self.plan.handle, C.byref(self.tens), self.ws.data_ptr(), float(lm),
                                                    float(ep), int(self.motion_only), self._stream()),
@@ -114,15 +124,20 @@ class CudaShardEngine:
 
 
 def ba_sharded(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, t1, iterations, lm, ep,
-               motion_only, group=None, engine_cls=CudaShardEngine, exchange=True, profile=None, collective="auto", plan=None):
+               motion_only, group=None, engine_cls=CudaShardEngine, exchange=True, profile=None, collective="auto", plan=None,
+               owned_inputs=False):
     """`slam_ext.ba` sharded by source keyframe across the ranks of `group`.
 
     `collective`: "allreduce" = one NCCL all-reduce of the reduced camera system per iteration; "nvls" = no collective
-    launch at all, the sum is formed by the NVSwitch inside the Cholesky kernel's loads (PeerSystem above); "auto" =
-    "nvls" where it is available (CUDA engine, multicast memory, more than 128 unknowns), else "allreduce".
+    launch at all, the sum is formed by the NVSwitch inside the Cholesky kernel's loads (PeerSystem above); "nvls2" = the
+    same in-switch sum as a small kernel of its own (every rank reduces 1/world of the tiles with multimem.ld_reduce and
+    multicasts them to all ranks with multimem.st) followed by a solve on local memory; "auto" = "nvls" on 2 GPUs,
+    "nvls2" from 4 GPUs on (the fused loads cost the solve 0.14 ms at 8 GPUs), "allreduce" where multicast memory is missing.
 
-    Every rank passes the full tensors (poses are replicated; for targets/weights only the rows of owned edges are
-    read).  On return `poses` is identical on all ranks and, if `exchange`, so are `disps[kx]` and `dz`.
+    `owned_inputs`: `targets` / `weights` hold only the rows of this rank's edges, [n_owned, 2, ht, wd] in the order of
+    `plan.owned_edges()` (a rank holds the inputs of its edges); otherwise every rank passes the
+    full tensors and reads only its rows.  Poses, disparities, eta are replicated either way.  On return `poses` is identical
+    on all ranks and, if `exchange`, so are `disps[kx]` and `dz`.
 
     `profile`: optional dict; CUDA event pairs around (linearise | all-reduce | solve+update) of every iteration are
     appended to profile["events"] and the plan is stored in profile["plan"] (bench.py reads them after a sync)."""
@@ -135,22 +150,34 @@ def ba_sharded(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, 
     if plan is None:
         plan = slam_ext.ba_plan(ii, jj, N, ht, wd, t0, t1, rank, world)
     eng = engine_cls(plan, poses, disps, intrinsics, disps_sens, targets, weights, eta, motion_only)
-    peer = None
-    if world > 1 and engine_cls is CudaShardEngine and collective in ("auto", "nvls"):
+    if owned_inputs:
+        n_own = int(plan.owned_edges().numel())
+        if tuple(targets.shape) != (n_own, 2, ht, wd) or tuple(weights.shape) != (n_own, 2, ht, wd):
+            raise RuntimeError(f"owned_inputs: targets/weights must be [{n_own},2,{ht},{wd}] (rows of plan.owned_edges())")
+    peer, two_step = None, False
+    if world > 1 and engine_cls is CudaShardEngine and collective in ("auto", "nvls", "nvls2"):
         if nvls_available(plan, poses.device, group):
             peer = PeerSystem.get(plan, poses.device, group)
-        elif collective == "nvls":
-            raise RuntimeError("collective='nvls' needs NVSwitch multicast memory and more than 128 unknowns")
+            two_step = collective == "nvls2" or (collective == "auto" and world >= 4)
+        elif collective in ("nvls", "nvls2"):
+            raise RuntimeError(f"collective='{collective}' needs NVSwitch multicast memory and more than 128 unknowns")
     if profile is not None:
         profile["plan"] = plan
-        profile["collective"] = "nvls" if peer is not None else "allreduce"
+        profile["collective"] = ("nvls2" if two_step else "nvls") if peer is not None else "allreduce"
         ev = profile.setdefault("events", [])
+    if hasattr(eng, "use_owned_rows"):
+        eng.use_owned_rows(bool(owned_inputs))
+    elif owned_inputs:
+        raise RuntimeError("this engine does not take owner-only inputs")
     try:
+        if two_step:  # accumulate in buffer 0, solve in this rank's instance of the reduced system
+            eng.use_peer_buffer(peer.bufs[0].data_ptr(), peer.hdls[0].multicast_ptr)
+            eng.use_solve_buffer(peer.bufs[2].data_ptr())
         for _ in range(int(iterations)):
             if profile is not None:
                 e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
                 e[0].record()
-            if peer is not None:
+            if peer is not None and not two_step:
                 b = peer.k & 1
                 eng.use_peer_buffer(peer.bufs[b].data_ptr(), peer.hdls[b].multicast_ptr)
                 peer.k += 1
@@ -159,6 +186,9 @@ def ba_sharded(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, 
                 e[1].record()
             if peer is not None:
                 peer.hdls[0].barrier(channel=0)  # every rank's partial system is complete and visible
+                if two_step:
+                    eng.peer_reduce(peer.hdls[0].multicast_ptr, peer.hdls[2].multicast_ptr, rank, world)
+                    peer.hdls[0].barrier(channel=0)  # every rank's share of the sum has landed everywhere
             elif world > 1:
                 dist.all_reduce(system, op=dist.ReduceOp.SUM, group=group)
             if profile is not None:
@@ -170,19 +200,35 @@ def ba_sharded(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, 
     finally:
         if peer is not None:
             eng.use_peer_buffer(None, None)
+            if two_step:
+                eng.use_solve_buffer(None)
+        if owned_inputs and hasattr(eng, "use_owned_rows"):
+            eng.use_owned_rows(False)
     if exchange and world > 1 and not motion_only:
         exchange_owned_rows(plan, disps, eng.dz, group)
     return [eng.dx, eng.dz]
 
 
 def exchange_owned_rows(plan, disps, dz, group=None):
-    """Make disps[kx] and dz identical on all ranks: every rank contributes the rows it owns."""
-    lo, hi = plan.owned_range()
+    """Make disps[kx] and dz identical on all ranks: an all-gather of the rows each rank owns (shards differ in size, so the
+    rows travel in slots of the largest shard)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
     kx = plan.kx.to(disps.device)
     HW = plan.ht * plan.wd
-    buf = torch.zeros(2, plan.K, HW, dtype=disps.dtype, device=disps.device)
-    buf[0, lo:hi] = disps.view(-1, HW)[kx[lo:hi]]
-    buf[1, lo:hi] = dz[lo:hi]
-    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-    disps.view(-1, HW)[kx] = buf[0]
-    dz.copy_(buf[1])
+    ranges = [plan.owned_range(r) for r in range(world)]
+    m = max(hi - lo for lo, hi in ranges)
+    if m == 0:
+        return
+    lo, hi = ranges[rank]
+    mine = torch.zeros(2, m, HW, dtype=disps.dtype, device=disps.device)
+    mine[0, : hi - lo] = disps.view(-1, HW)[kx[lo:hi]]
+    mine[1, : hi - lo] = dz[lo:hi]
+    allrows = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allrows, mine, group=group)
+    dflat = disps.view(-1, HW)
+    for r, (rlo, rhi) in enumerate(ranges):
+        if r == rank or rhi == rlo:
+            continue
+        dflat[kx[rlo:rhi]] = allrows[r][0, : rhi - rlo]
+        dz[rlo:rhi] = allrows[r][1, : rhi - rlo]

@@ -63,6 +63,11 @@ def ba_plan(ii: torch.Tensor, jj: torch.Tensor, n_frames: int, ht: int, wd: int,
     return plan
 
 
+def _aligned(t: torch.Tensor, align: int = 16) -> torch.Tensor:
+    """`t` itself when its storage address is `align`-byte aligned, else a copy in freshly allocated (aligned) storage."""
+    return t if t.data_ptr() % align == 0 else t.clone(memory_format=torch.contiguous_format)
+
+
 def _tensors(poses, disps, intrinsics, disps_sens, targets, weights, eta, dx, dz, motion_only):
     t = _lib.Tensors()
     t.poses = poses.data_ptr()
@@ -117,11 +122,24 @@ def ba(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, 
 
     Runs `iterations` Gauss-Newton steps on the device without host synchronisation inside the loop, updates
     `poses[t0:t1]` and `disps[kx]` in place and returns `[dx, dz]` of the last iteration
-    (`dx[t1-t0, 6]`, `dz[K, ht*wd]`; `dz` is an empty tensor when `motion_only`, where the reference returns an
-    undefined one)."""
+    (`dx[t1-t0, 6]`, `dz[K, ht*wd]`; `dz` is None when `motion_only`: the reference returns an undefined tensor, which reaches
+    Python as None)."""
     t0, t1, iterations = int(t0), int(t1), int(iterations)
     dev, N, ht, wd, E = validate(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, t1, motion_only)
     motion_only = bool(motion_only)
+    # The kernels use 8/16-byte vector loads and 16-byte bulk copies on the pixel arrays.  Torch allocations are 512-byte
+    # aligned, but a contiguous VIEW at an odd storage offset (a sliced eta, a from_blob tensor) is not, and a misaligned
+    # vector access is a sticky CUDA fault.  The reference's scalar accessors take such inputs, so they are accepted here
+    # too: read-only inputs are copied to aligned storage, in/out tensors are updated through an aligned copy.
+    disps_arg = disps
+    disps, disps_sens, targets, weights = _aligned(disps), _aligned(disps_sens), _aligned(targets), _aligned(weights)
+    if eta is not None and torch.is_tensor(eta) and eta.numel() > 0:
+        eta = _aligned(eta)
+    if disps is not disps_arg:
+        try:
+            return ba(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, t1, iterations, lm, ep, motion_only, plan)
+        finally:
+            disps_arg.copy_(disps)
     if plan is None:
         plan = ba_plan(ii, jj, N, ht, wd, t0, t1)  # at most one D2H of the edge list per call (the reference does >= 12 per iteration)
     elif (plan.E, plan.N, plan.ht, plan.wd, plan.t0, plan.t1) != (E, N, ht, wd, t0, t1):
@@ -137,14 +155,14 @@ def ba(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj, t0, 
         eta = eta.contiguous()
         dz = torch.zeros(K, HW, dtype=torch.float32, device=dev)
     if iterations <= 0 or P <= 0:
-        return [dx, dz if dz is not None else torch.empty(0, device=dev)]
+        return [dx, dz]
     with torch.cuda.device(dev):
         ws = plan.workspace(dev)
         tens = _tensors(poses, disps, intrinsics, disps_sens, targets, weights, eta, dx, dz, motion_only)
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(_lib.lib().vipe_ba_run(plan.handle, C.byref(tens), ws.data_ptr(), iterations, float(lm), float(ep),
                                           int(motion_only), stream), "vipe_ba_run")
-    return [dx, dz if dz is not None else torch.empty(0, device=dev)]
+    return [dx, dz]
 
 
 _BATCH_PLANS: dict = {}
@@ -201,7 +219,7 @@ def ba_batch(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, jj
             tens = _tensors(poses, disps, intrinsics, disps_sens, targets, weights, eta, dx, dz, motion_only)
             _lib.check(_lib.lib().vipe_ba_run(plan.handle, C.byref(tens), ws.data_ptr(), int(iterations), float(lm), float(ep),
                                               int(motion_only), torch.cuda.current_stream(dev).cuda_stream), "vipe_ba_run")
-    return [dx, dz if dz is not None else torch.empty(0, device=dev)]
+    return [dx, dz]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -126,6 +126,15 @@ class BAPlan:
             self._ws[key] = ws
         return ws
 
+    def owned_edges(self) -> torch.Tensor:
+        """Edge ids of this rank's shard in the order owner-only `targets` / `weights` rows must have (CSR order over the owned
+        source frames), int64 host tensor."""
+        n = int(_lib.lib().vipe_ba_plan_num_owned_edges(self._h))
+        out = torch.empty(max(n, 0), dtype=torch.int64)
+        if n > 0:
+            _lib.check(_lib.lib().vipe_ba_plan_copy_owned_edges(self._h, out.data_ptr()), "copy_owned_edges")
+        return out
+
     @property
     def sys_order(self) -> torch.Tensor:
         """Position of each free pose in the reduced camera system (a fill-reducing elimination order), [P] int64."""

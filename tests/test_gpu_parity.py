@@ -64,8 +64,13 @@ def test_full_ba_parity(slam_ext, dev, name):
         if f not in kx:
             assert torch.equal(r["a"][1][f].cpu(), pr.disps[f])
     # last-iteration updates
-    if name != "c3":  # at C3 the 8th update is at the fp32 noise floor of the weakly constrained directions
+    # last-iteration update.  At C3 the 8th update has shrunk to the fp32 noise floor of the weakly constrained (gauge)
+    # directions, so it is bounded in absolute terms there: the difference is below the size of a 1e-4 relative pose change
+    if name != "c3":
         assert (r["dx"].cpu().double() - r["dxr"]).norm() <= 2e-2 * r["dxr"].norm() + 1e-7
+    else:
+        scale = r["ref"][0][pr.t0: pr.t1, :3].double().norm()
+        assert (r["dx"].cpu().double() - r["dxr"]).norm() <= 1e-4 * scale, ((r["dx"].cpu().double() - r["dxr"]).norm(), scale)
     assert r["dz"].shape == (len(kx), pr.cfg.ht * pr.cfg.wd)
 
 
@@ -253,20 +258,23 @@ def test_full_size_properties(slam_ext, dev, name):
     assert pose_errors(a[0], before, pr2.t0, pr2.t1)[0] < 1e-3
 
 
-def test_plan_cache_and_repeat_calls_are_deterministic(slam_ext, dev):
-    pr = make_problem("c2")
+@pytest.mark.parametrize("name", ["c2", "c3"])
+def test_plan_cache_and_repeat_calls_are_deterministic(slam_ext, dev, name):
+    pr = make_problem(name)
     outs = []
     for _ in range(2):
         a = pr.args(dev)
         slam_ext.ba(*a)
         outs.append((a[0].cpu(), a[1].cpu()))
-    # fp64 atomics into the reduced system make the sum order vary; results agree to fp32 rounding of dx
-    assert pose_errors(outs[0][0], outs[1][0], pr.t0, pr.t1)[0] < 1e-6
+    # the reduced system is assembled in a fixed order (assemble_kernel) and every other sum is a fixed-shape tree:
+    # repeated calls are bit-identical, like the reference's Eigen assembly
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
-def test_c4_two_iterations_vs_reference_run(slam_ext, dev):
-    """Full-size C4 (1000 keyframes, 12000 edges, 64x112): two Gauss-Newton iterations against the REFERENCE's own CUDA
-    slam_ext.ba (oracle/_ref) on the same inputs -- the fp64 oracle needs >10 GB and minutes at this size."""
+@pytest.mark.parametrize("iters", [2, 8])
+def test_c4_vs_reference_run(slam_ext, dev, iters):
+    """Full-size C4 (1000 keyframes, 12000 edges, 64x112): two and all eight Gauss-Newton iterations against the REFERENCE's
+    own CUDA slam_ext.ba (oracle/_ref) on the same inputs -- the fp64 oracle needs >10 GB and minutes at this size."""
     from oracle import build_ref
 
     mod = build_ref.load()
@@ -274,7 +282,7 @@ def test_c4_two_iterations_vs_reference_run(slam_ext, dev):
         pytest.skip("oracle/_ref/vipe_ref_ext.so not built")
     pr = make_problem("c4")
     a, b = pr.args(dev), pr.args(dev)
-    a[11] = b[11] = 2
+    a[11] = b[11] = iters
     dxr, dzr = mod.slam_ext.ba(*a)
     dx, dz = slam_ext.ba(*b)
     torch.cuda.synchronize()
@@ -283,7 +291,8 @@ def test_c4_two_iterations_vs_reference_run(slam_ext, dev):
     de = disp_error(b[1], a[1], kx)
     print("C4 vs reference run:", te, re_, de, float((dx - dxr).norm() / dxr.norm()), float((dz - dzr).norm() / dzr.norm()))
     assert te <= TOL_T and re_ <= TOL_R and de <= TOL_D, (te, re_, de)
-    assert (dx - dxr).norm() <= 5e-2 * dxr.norm()
+    if iters == 2:  # (after 8 iterations the update itself is at the noise floor)
+        assert (dx - dxr).norm() <= 5e-2 * dxr.norm()
 
 
 @pytest.mark.parametrize("motion_only", [True, False])
@@ -320,6 +329,56 @@ def test_batched_clips_match_per_clip_oracle(slam_ext, dev, motion_only):
         else:
             assert disp_error(a[1][c * N:(c + 1) * N], ref[1], tr.bk.kx) <= TOL_D
         assert (dx[c * 7:(c + 1) * 7].cpu().double() - dxr).norm() <= 2e-2 * dxr.norm() + 1e-7
+
+
+@pytest.mark.parametrize("name", ["c2", "c3"])
+def test_tensor_core_pipeline_parity(slam_ext, dev, name, monkeypatch):
+    """VIPE_BA_LIN3=2 routes the full linearisation of frames with <= 10 edges through the tcgen05 / TMEM pipeline
+    (ba_lin3.cu: TMA stages, TF32 hi/lo Gram in tensor memory); same bounds as the default path.  At C3 the frames with
+    more edges run the FMA kernel in the same iteration, so the two kernels' partial records are mixed."""
+    from vipe_b200 import plan as plan_mod
+
+    monkeypatch.setenv("VIPE_BA_LIN3", "2")
+    plan_mod._CACHE.clear()
+    slam_ext._LAST_PLANS.clear()
+    try:
+        pr = make_problem(name)
+        r = _compare(slam_ext, dev, pr)
+        print(f"[tc parity {name}] translation rel {r['te']:.2e}  rotation max {r['re']:.2e} rad  disparity rel {r['de']:.2e}")
+        assert r["te"] <= TOL_T and r["re"] <= TOL_R and r["de"] <= TOL_D, (r["te"], r["re"], r["de"])
+    finally:
+        plan_mod._CACHE.clear()
+        slam_ext._LAST_PLANS.clear()
+
+
+def test_c5_real_configuration(slam_ext, dev):
+    """BASELINE config 5 as specified: 64 independent clips of the C2 shape (16 keyframes, 120 edges, 48x64), motion-only,
+    4 Gauss-Newton iterations, ONE batched call; a sample of the clips is checked against the fp64 oracle run per clip."""
+    from vipe_b200.synthetic import CONFIGS
+
+    cfg = CONFIGS["c5"]
+    clips = [make_problem(cfg, clip=c) for c in range(cfg.clips)]
+    N, nc = cfg.n_frames, cfg.clips
+    cat = lambda xs: torch.cat(xs, dim=0)
+    pr = clips[0]
+    a = [cat([p.poses for p in clips]).to(dev), cat([p.disps for p in clips]).to(dev), pr.intrinsics.to(dev),
+         cat([p.disps_sens for p in clips]).to(dev), cat([p.targets for p in clips]).to(dev), cat([p.weights for p in clips]).to(dev),
+         cat([p.eta for p in clips]).to(dev), cat([p.ii + c * N for c, p in enumerate(clips)]).to(dev),
+         cat([p.jj + c * N for c, p in enumerate(clips)]).to(dev)]
+    d0 = a[1].clone()
+    dx, dz = slam_ext.ba_batch(*a, [c * N for c in range(nc + 1)], [c * N + pr.t0 for c in range(nc)],
+                               [c * N + pr.t1 for c in range(nc)], cfg.iters, cfg.lm, cfg.ep, True)
+    torch.cuda.synchronize()
+    assert torch.equal(a[1], d0), "motion-only must not touch disparities"
+    P = pr.t1 - pr.t0
+    for c in (0, 1, 17, 40, 63):
+        ref = clips[c].args()
+        dxr, _ = O.ba(*ref, dtype=torch.float64)
+        pc = a[0][c * N:(c + 1) * N]
+        te, re_ = pose_errors(pc, ref[0], pr.t0, pr.t1)
+        assert te <= TOL_T and re_ <= TOL_R, (c, te, re_)
+        assert torch.equal(pc[: pr.t0].cpu(), clips[c].poses[: pr.t0])
+        assert (dx[c * P:(c + 1) * P].cpu().double() - dxr).norm() <= 2e-2 * dxr.norm() + 1e-7
 
 
 def _hub_problem(n_frames, ht=24, wd=32):

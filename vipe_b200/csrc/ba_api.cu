@@ -72,6 +72,12 @@ struct vipe_ba_plan {
     // pose_sys[f] = position of pose f in the reduced system (the natural order, see compute_elimination_order), rowmap[s] = index
     // of system unknown s in the dx output, tstruct[i * T + j] = 1 when tile (i, j) of the Cholesky factor can be non-zero
     std::vector<int> pose_sys, rowmap;
+    // deterministic assembly (see assemble_kernel): contribution slots per frame and, per destination, the slots to add
+    std::vector<long long> cbase, vbase, bdst_off, vdst_off;
+    std::vector<int> bdst_ld, bsrc_ptr, bsrc, vdst_adiag, vsrc_ptr, vsrc;
+    long long n_cblk = 0, n_cvec = 0;
+    size_t off_cbase = 0, off_vbase = 0, off_bdst_off = 0, off_bdst_ld = 0, off_bsrc_ptr = 0, off_bsrc = 0, off_vdst_off = 0,
+           off_vdst_adiag = 0, off_vsrc_ptr = 0, off_vsrc = 0, off_cblk = 0, off_cvec = 0, off_cvec2 = 0;
     std::vector<unsigned char> tstruct;
     bool ordered = false;
     size_t off_psys = 0, off_rowmap = 0, off_tstruct = 0;
@@ -224,6 +230,92 @@ static void compute_elimination_order(vipe_ba_plan *p) {
     p->ordered = true;
 }
 
+
+// Contribution slots and destination lists of the deterministic assembly.  Frame k (owned, d edges, source pose i, targets
+// j_m) owns block slots [cbase, cbase + npairs + d + 1): the pair blocks M(m, m') in pair order, the d blocks T(m') of the
+// source row, the block Z of (i, i); and vector slots [vbase, vbase + d + 1): g_m per edge, then the source's.  Destinations
+// list their slots in ascending slot order (= by source frame, then by position), which fixes the summation order.
+static void build_assembly_lists(vipe_ba_plan *p) {
+    const int K = p->K;
+    p->cbase.assign(K + 1, 0);
+    p->vbase.assign(K + 1, 0);
+    for (int k = 0; k < K; k++) {
+        const long long d = p->fptr[k + 1] - p->fptr[k];
+        const bool owned = k >= p->k_lo && k < p->k_hi && d > 0;
+        p->cbase[k + 1] = p->cbase[k] + (owned ? d * (d + 1) / 2 + d + 1 : 0);
+        p->vbase[k + 1] = p->vbase[k] + (owned ? d + 1 : 0);
+    }
+    p->n_cblk = p->cbase[K];
+    p->n_cvec = p->vbase[K];
+    struct BSrc { long long key; int src; };
+    std::vector<BSrc> bl, vl;
+    // key of a block destination: (problem, row pose, column pose) with row >= column
+    auto add_block = [&](int prob, int pa, int pb, long long slot, bool transposed_if_swapped) {
+        (void)transposed_if_swapped;
+        int hi = pa, lo = pb, tr = 0;
+        if (pa < pb) hi = pb, lo = pa, tr = 1;
+        const long long key = ((long long)prob << 48) | ((long long)hi << 24) | (long long)lo;
+        bl.push_back({key, (int)(slot * 2 + tr)});
+    };
+    std::vector<int> aj;
+    for (int k = p->k_lo; k < p->k_hi; k++) {
+        const int s0 = p->fptr[k], d = p->fptr[k + 1] - s0;
+        if (d == 0) continue;
+        const int f = (int)p->kx[k];
+        const int prob = p->frame_prob[k], ai = p->pose_sys[f];
+        aj.assign(d, -1);
+        for (int m = 0; m < d; m++) {
+            const int j = p->e_jj[p->fedge[s0 + m]];
+            if (j != f) aj[m] = p->pose_sys[j];  // stereo edges (i == j) carry no pose block
+        }
+        const long long cb = p->cbase[k], vb = p->vbase[k];
+        const int npairs = d * (d + 1) / 2;
+        for (int mp = 0; mp < d; mp++)
+            for (int m = 0; m <= mp; m++) {
+                const long long slot = cb + (long long)mp * (mp + 1) / 2 + m;
+                const int pa = aj[m], pb = aj[mp];
+                if (pa < 0 || pb < 0) continue;
+                add_block(prob, pa, pb, slot, true);
+                if (m != mp && pa == pb) bl.push_back({((long long)prob << 48) | ((long long)pa << 24) | pa, (int)(slot * 2 + 1)});  // M + M^T
+            }
+        if (ai >= 0) {
+            for (int mp = 0; mp < d; mp++)
+                if (aj[mp] >= 0) add_block(prob, ai, aj[mp], cb + npairs + mp, true);
+            add_block(prob, ai, ai, cb + npairs + d, false);
+        }
+        for (int m = 0; m < d; m++)
+            if (aj[m] >= 0) vl.push_back({((long long)prob << 32) | aj[m], (int)(vb + m)});
+        if (ai >= 0) vl.push_back({((long long)prob << 32) | ai, (int)(vb + d)});
+    }
+    auto by_key = [](const BSrc &x, const BSrc &y) { return x.key != y.key ? x.key < y.key : x.src < y.src; };
+    std::sort(bl.begin(), bl.end(), by_key);
+    std::sort(vl.begin(), vl.end(), by_key);
+    p->bdst_off.clear(), p->bdst_ld.clear(), p->bsrc_ptr.assign(1, 0), p->bsrc.clear();
+    for (size_t q = 0; q < bl.size(); q++) {
+        if (q == 0 || bl[q].key != bl[q - 1].key) {
+            if (q) p->bsrc_ptr.push_back((int)p->bsrc.size());
+            const int prob = (int)(bl[q].key >> 48), hi = (int)((bl[q].key >> 24) & 0xFFFFFF), lo = (int)(bl[q].key & 0xFFFFFF);
+            const long long n = p->prob_npad[prob];
+            p->bdst_off.push_back(p->prob_hoff[prob] + (long long)(6 * hi) * n + 6 * lo);
+            p->bdst_ld.push_back((int)n);
+        }
+        p->bsrc.push_back(bl[q].src);
+    }
+    if (!bl.empty()) p->bsrc_ptr.push_back((int)p->bsrc.size());
+    p->vdst_off.clear(), p->vdst_adiag.clear(), p->vsrc_ptr.assign(1, 0), p->vsrc.clear();
+    for (size_t q = 0; q < vl.size(); q++) {
+        if (q == 0 || vl[q].key != vl[q - 1].key) {
+            if (q) p->vsrc_ptr.push_back((int)p->vsrc.size());
+            const int prob = (int)(vl[q].key >> 32), pose = (int)(vl[q].key & 0xFFFFFFFF);
+            const long long n = p->prob_npad[prob];
+            p->vdst_off.push_back(p->prob_hoff[prob] + n * n + 6 * pose);
+            p->vdst_adiag.push_back((int)n);
+        }
+        p->vsrc.push_back(vl[q].src);
+    }
+    if (!vl.empty()) p->vsrc_ptr.push_back((int)p->vsrc.size());
+}
+
 // C independent problems share one plan: problem c owns frames [frame_ptr[c], frame_ptr[c+1]) and optimises the poses
 // of its window [t0s[c], t1s[c]) (global frame ids).  C == 1 is the reference operator.
 static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edges, int64_t n_frames, int ht, int wd, int C,
@@ -365,6 +457,7 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     for (int k = p->k_lo; k < p->k_hi; k++) p->dmax = std::max(p->dmax, p->fptr[k + 1] - p->fptr[k]);
 
     compute_elimination_order(p);
+    build_assembly_lists(p);
 
     if (tile_config2(p->HW, std::max(p->dmax, 1), false, p->NT)) {
         p->packed = true;
@@ -448,6 +541,16 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     p->off_flist_tc = take(sizeof(int) * std::max<size_t>(p->flist_tc.size(), 1));
     p->off_flist_rest = take(sizeof(int) * std::max<size_t>(p->flist_rest.size(), 1));
     p->off_psys = take(sizeof(int) * n_frames);
+    p->off_cbase = take(sizeof(long long) * (K + 1));
+    p->off_vbase = take(sizeof(long long) * (K + 1));
+    p->off_bdst_off = take(sizeof(long long) * std::max<size_t>(p->bdst_off.size(), 1));
+    p->off_bdst_ld = take(sizeof(int) * std::max<size_t>(p->bdst_ld.size(), 1));
+    p->off_bsrc_ptr = take(sizeof(int) * std::max<size_t>(p->bsrc_ptr.size(), 1));
+    p->off_bsrc = take(sizeof(int) * std::max<size_t>(p->bsrc.size(), 1));
+    p->off_vdst_off = take(sizeof(long long) * std::max<size_t>(p->vdst_off.size(), 1));
+    p->off_vdst_adiag = take(sizeof(int) * std::max<size_t>(p->vdst_adiag.size(), 1));
+    p->off_vsrc_ptr = take(sizeof(int) * std::max<size_t>(p->vsrc_ptr.size(), 1));
+    p->off_vsrc = take(sizeof(int) * std::max<size_t>(p->vsrc.size(), 1));
     p->off_rowmap = take(sizeof(int) * p->npad);
     p->off_tstruct = take(std::max<size_t>(p->tstruct.size(), 1));
     p->idx_bytes = off;
@@ -463,6 +566,9 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     p->off_qw = take(sizeof(float) * (size_t)K * p->HW);
     p->off_sys = take(sizeof(double) * p->sys_doubles);  // per problem [H ; b ; diag(A)]
     p->off_dx = take(sizeof(double) * ((size_t)p->npad + (size_t)p->npad * kCholBlock));  // 1/diag(L), then L_jj^-T tiles
+    p->off_cblk = take(sizeof(double) * 36 * (size_t)std::max<long long>(p->n_cblk, 1));
+    p->off_cvec = take(sizeof(double) * 6 * (size_t)std::max<long long>(p->n_cvec, 1));
+    p->off_cvec2 = take(sizeof(double) * 6 * (size_t)std::max<long long>(p->n_cvec, 1));
     p->off_gdx = take(sizeof(float) * ((size_t)6 * std::max(P, 1) + 1));  // graph-owned dx / dz (see vipe_ba_run)
     p->off_gdz = take(sizeof(float) * (size_t)std::max(K, 1) * p->HW);
     p->off_flag = take(sizeof(int) * chol_scratch_ints(p->npad));
@@ -486,6 +592,19 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     std::memcpy(p->blob.data() + p->off_pn, p->prob_n.data(), sizeof(int) * C);
     std::memcpy(p->blob.data() + p->off_prow0, p->prob_row0.data(), sizeof(int) * C);
     std::memcpy(p->blob.data() + p->off_psys, p->pose_sys.data(), sizeof(int) * n_frames);
+    auto put = [&](size_t off, const void *src, size_t bytes) {
+        if (bytes) std::memcpy(p->blob.data() + off, src, bytes);
+    };
+    put(p->off_cbase, p->cbase.data(), sizeof(long long) * p->cbase.size());
+    put(p->off_vbase, p->vbase.data(), sizeof(long long) * p->vbase.size());
+    put(p->off_bdst_off, p->bdst_off.data(), sizeof(long long) * p->bdst_off.size());
+    put(p->off_bdst_ld, p->bdst_ld.data(), sizeof(int) * p->bdst_ld.size());
+    put(p->off_bsrc_ptr, p->bsrc_ptr.data(), sizeof(int) * p->bsrc_ptr.size());
+    put(p->off_bsrc, p->bsrc.data(), sizeof(int) * p->bsrc.size());
+    put(p->off_vdst_off, p->vdst_off.data(), sizeof(long long) * p->vdst_off.size());
+    put(p->off_vdst_adiag, p->vdst_adiag.data(), sizeof(int) * p->vdst_adiag.size());
+    put(p->off_vsrc_ptr, p->vsrc_ptr.data(), sizeof(int) * p->vsrc_ptr.size());
+    put(p->off_vsrc, p->vsrc.data(), sizeof(int) * p->vsrc.size());
     std::memcpy(p->blob.data() + p->off_rowmap, p->rowmap.data(), sizeof(int) * p->npad);
     if (!p->tstruct.empty()) std::memcpy(p->blob.data() + p->off_tstruct, p->tstruct.data(), p->tstruct.size());
     std::memcpy(p->blob.data() + p->off_slot_src, p->slot_src.data(), sizeof(int) * p->slot_src.size());
@@ -707,8 +826,30 @@ static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void 
     ra.msc = (double *)(w + p->off_msc);
     ra.hsys = H;
     ra.motion_only = motion_only;
+    ra.cblk = (double *)(w + p->off_cblk);
+    ra.cvec = (double *)(w + p->off_cvec);
+    ra.cvec2 = (double *)(w + p->off_cvec2);
+    ra.cbase = (const long long *)(w + p->off_cbase);
+    ra.vbase = (const long long *)(w + p->off_vbase);
     VBA_CUDA(launch_frame_reduce(ra, nframes, std::max(p->dmax, 1), st));
     p->launches++;
+    AssembleArgs aa;
+    aa.cblk = ra.cblk, aa.cvec = ra.cvec, aa.cvec2 = ra.cvec2;
+    aa.sys = H;
+    aa.bdst_off = (const long long *)(w + p->off_bdst_off);
+    aa.bdst_ld = (const int *)(w + p->off_bdst_ld);
+    aa.bsrc_ptr = (const int *)(w + p->off_bsrc_ptr);
+    aa.bsrc = (const int *)(w + p->off_bsrc);
+    aa.nb = (int)p->bdst_off.size();
+    aa.vdst_off = (const long long *)(w + p->off_vdst_off);
+    aa.vdst_adiag = (const int *)(w + p->off_vdst_adiag);
+    aa.vsrc_ptr = (const int *)(w + p->off_vsrc_ptr);
+    aa.vsrc = (const int *)(w + p->off_vsrc);
+    aa.nv = (int)p->vdst_off.size();
+    if (aa.nb + aa.nv > 0) {
+        VBA_CUDA(launch_assemble(aa, st));
+        p->launches++;
+    }
     return 0;
 }
 

@@ -114,9 +114,32 @@ struct ReduceArgs {
     float focal_lm = 0.0f;
     double *msc;   // M scratch (used when a frame's blocks do not fit shared memory)
     int msc_smem = 0;  // 1: M lives in the kernel's shared memory (set by launch_frame_reduce)
+    // Deterministic assembly: every frame writes its 6x6 block / 6-vector contributions to fixed slots of `cblk` / `cvec`
+    // (`cvec2`: the same slots for diag(A)); assemble_kernel then sums the slots of each destination in a fixed order.
+    double *cblk = nullptr;           // [sum over owned frames of (npairs + d + 1)][36]
+    double *cvec = nullptr, *cvec2 = nullptr;  // [sum over owned frames of (d + 1)][6]
+    const long long *cbase = nullptr;  // [K] first block slot of frame k
+    const long long *vbase = nullptr;  // [K] first vector slot of frame k
     double *hsys;  // per problem: [n*n] row-major lower triangle (+ full diagonal blocks), then b [n], then diag(A) [n]
                    //   (diag(A): the pose Hessian alone, before the Schur complement, for damp_on_pose_hessian)
     int motion_only;
+};
+
+// Destinations of the deterministic assembly (built by the plan): dst_off = element (0,0) of the 6x6 block / first of the 6 vector
+// entries inside the system buffer, src = contribution slots (blocks: slot * 2 + transposed).
+struct AssembleArgs {
+    const double *cblk, *cvec, *cvec2;
+    double *sys;
+    const long long *bdst_off;  // [nb]
+    const int *bdst_ld;         // [nb] row stride (npad of the problem)
+    const int *bsrc_ptr;        // [nb + 1]
+    const int *bsrc;            // [...]
+    int nb;
+    const long long *vdst_off;  // [nv] offset of the rhs entries; diag(A) lives vdst_adiag[] further
+    const int *vdst_adiag;      // [nv] distance from the rhs entries to the diag(A) entries
+    const int *vsrc_ptr;        // [nv + 1]
+    const int *vsrc;            // [...]
+    int nv;
 };
 
 struct BackArgs {

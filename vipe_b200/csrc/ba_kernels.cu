@@ -364,6 +364,7 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
     double *const bsys = hsys + (size_t)n * n;
     double *const adiag = bsys + n;
     const int ai = tb.pose_sys[src];
+    const size_t cb = (size_t)a.cbase[k], vb = (size_t)a.vbase[k];
 
     double *G = dsm;            // [d][36]
     double *T = G + d * 36;     // [d][36]
@@ -400,7 +401,9 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
         const double s = a.motion_only ? 0.0 : tile_sum(gp + npairs * 36 + idx, rec, ntile);
         const double g = hs[m * kEdgeVals + 20 + r] - s;
         gv[idx] = g;
-        if (aj[m] >= 0) atomicAdd(bsys + 6 * aj[m] + r, g);
+        a.cvec[(vb + m) * 6 + r] = g;  // -> rhs(j_m)
+        const int sl = hslot(r, r);
+        a.cvec2[(vb + m) * 6 + r] = sl >= 0 ? hs[m * kEdgeVals + sl] : 0.0;  // -> diag(A)(j_m): H_jj,m alone
     }
     // M blocks
     for (int idx = tid; idx < npairs * 36; idx += NT) {
@@ -414,20 +417,9 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
             const int hi = r >= c ? r : c, lo = r >= c ? c : r;
             const int sl = hslot(hi, lo);
             if (sl >= 0) v += hs[m * kEdgeVals + sl];
-            if (r == c && sl >= 0 && aj[m] >= 0) atomicAdd(adiag + 6 * aj[m] + r, hs[m * kEdgeVals + sl]);
         }
         msc[idx] = v;
-        const int pa = aj[m], pb = aj[mp];
-        if (pa >= 0 && pb >= 0) {
-            if (m == mp) {
-                atomicAdd(hsys + (size_t)(6 * pa + r) * n + 6 * pa + c, v);
-            } else if (pa == pb) {  // two edges into the same target pose: M + M^T on the diagonal block
-                atomicAdd(hsys + (size_t)(6 * pa + r) * n + 6 * pa + c, v);
-                atomicAdd(hsys + (size_t)(6 * pa + c) * n + 6 * pa + r, v);
-            } else {
-                add_block_entry(hsys, n, pa, r, pb, c, v);
-            }
-        }
+        a.cblk[(cb + p) * 36 + rc] = v;  // -> block (j_m, j_m') (and its transpose when both edges reach the same pose)
     }
     // Focal length (one more variable, row/column `focal_row` of the reduced system):
     //   H(f, j_m) += J_j^T w J_f - sum_px Q u_f u_m,  H(f,f) += (1 + lm_f) J_f^T w J_f - sum_px Q u_f^2,  b(f) += J_f^T w r - sum_px Q w u_f
@@ -485,7 +477,7 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
             }
         }
         T[idx] = s;
-        if (aj[mp] >= 0) add_block_entry(hsys, n, ai, r, aj[mp], c, s);
+        a.cblk[(cb + npairs + mp) * 36 + rc] = s;  // -> block (i, j_m')
     }
     __syncthreads();
     // Z = sum_m' T_m' G_m'^T  -> block (i,i);   rhs(i) += sum_m G_m g_m
@@ -496,7 +488,7 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
 #pragma unroll
             for (int q = 0; q < 6; q++) s += T[mp * 36 + r * 6 + q] * G[mp * 36 + c * 6 + q];
         }
-        atomicAdd(hsys + (size_t)(6 * ai + r) * n + 6 * ai + c, s);
+        a.cblk[(cb + npairs + d) * 36 + tid] = s;  // -> block (i, i)
     } else if (tid >= 64 && tid < 70) {
         const int r = tid - 64;
         double s = 0.0;
@@ -504,7 +496,7 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
 #pragma unroll
             for (int q = 0; q < 6; q++) s += G[m * 36 + r * 6 + q] * gv[m * 6 + q];
         }
-        atomicAdd(bsys + 6 * ai + r, s);
+        a.cvec[(vb + d) * 6 + r] = s;  // -> rhs(i)
     } else if (tid >= 128 && tid < 134) {
         if (a.fpart) {  // H(f, i) += sum_m G_m c_m
             const int r = tid - 128;
@@ -527,8 +519,45 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
                     if (sl >= 0) s += Gm[p] * hs[m * kEdgeVals + sl] * Gm[q];
                 }
         }
-        atomicAdd(adiag + 6 * ai + r, s);
+        a.cvec2[(vb + d) * 6 + r] = s;  // -> diag(A)(i)
     }
+}
+
+// Deterministic assembly of the reduced camera system: one 36-thread group per destination block (6 threads per destination
+// vector) adds up its contribution slots in the order the plan lists them -- sorted by source frame, then by slot -- so the
+// result does not depend on scheduling (the reference's Eigen assembly is deterministic as well).
+__global__ void __launch_bounds__(252) assemble_kernel(const AssembleArgs a) {
+    const int grp = threadIdx.x / 36, rc = threadIdx.x - grp * 36;
+    const int nbg = (a.nb + 6) / 7;
+    if ((int)blockIdx.x < nbg) {
+        const int b = blockIdx.x * 7 + grp;
+        if (b >= a.nb) return;
+        const int r = rc / 6, c = rc - r * 6, rct = c * 6 + r;
+        double s = 0.0;
+        for (int q = a.bsrc_ptr[b]; q < a.bsrc_ptr[b + 1]; q++) {
+            const int src = a.bsrc[q];
+            s += a.cblk[(size_t)(src >> 1) * 36 + ((src & 1) ? rct : rc)];
+        }
+        a.sys[a.bdst_off[b] + (long long)r * a.bdst_ld[b] + c] += s;
+    } else {
+        const int v = ((int)blockIdx.x - nbg) * 42 + threadIdx.x / 6, r = threadIdx.x % 6;
+        if (v >= a.nv) return;
+        double s = 0.0, s2 = 0.0;
+        for (int q = a.vsrc_ptr[v]; q < a.vsrc_ptr[v + 1]; q++) {
+            const int src = a.vsrc[q];
+            s += a.cvec[(size_t)src * 6 + r];
+            s2 += a.cvec2[(size_t)src * 6 + r];
+        }
+        a.sys[a.vdst_off[v] + r] += s;
+        a.sys[a.vdst_off[v] + a.vdst_adiag[v] + r] += s2;
+    }
+}
+
+cudaError_t launch_assemble(const AssembleArgs &a, cudaStream_t st) {
+    const int grid = (a.nb + 6) / 7 + (a.nv + 41) / 42;
+    if (grid <= 0) return cudaSuccess;
+    assemble_kernel<<<grid, 252, 0, st>>>(a);
+    return cudaGetLastError();
 }
 
 // =================================================================================================

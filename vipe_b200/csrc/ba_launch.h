@@ -29,6 +29,7 @@ cudaError_t launch_lin3(const LinArgs &a, const Lin3Item *items_dev, int nframes
 cudaError_t launch_lin3_motion(const LinArgs &a, const int *slot_src_dev, int slot_lo, int nslots, int chunk_px, float *econst_dev,
                                int num_sms, cudaStream_t st);
 cudaError_t launch_frame_reduce(const ReduceArgs &a, int nframes, int dmax, cudaStream_t st);
+cudaError_t launch_assemble(const AssembleArgs &a, cudaStream_t st);
 cudaError_t launch_backsub(const BackArgs &a, int nframes, int dmax, cudaStream_t st);
 // `intr` non-null: also apply the focal step dx[focal_row] * focal_jscale to fx and fy
 cudaError_t launch_pose_retr(float *poses, const float *dx, const int *pose_row, int n_poses, int renorm, float *intr,

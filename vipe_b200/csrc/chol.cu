@@ -656,10 +656,13 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
                     acc[mt][0] = v.x, acc[mt][1] = v.y;
                 }
                 if (i == j && i0 + r < a.n && (r == c || r == c + 1)) {
-                    const int e = (r == c) ? 0 : 1;
-                    double dd = acc[mt][e];
+                    // (static indices only: a run-time index would move the whole accumulator array to local memory)
+                    const bool first = (r == c);
+                    double dd = first ? acc[mt][0] : acc[mt][1];
                     if (a.dampdiag) dd = a.Ain ? mc_load_sum(a.Ain + (size_t)ld * ld + ld + i0 + r) : a.dampdiag[i0 + r];
-                    acc[mt][e] += (double)a.ep + (double)a.lm * dd;
+                    const double add = (double)a.ep + (double)a.lm * dd;
+                    acc[mt][0] += first ? add : 0.0;
+                    acc[mt][1] += first ? 0.0 : add;
                 }
             }
         }

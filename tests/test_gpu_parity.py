@@ -333,12 +333,13 @@ def test_batched_clips_match_per_clip_oracle(slam_ext, dev, motion_only):
 
 @pytest.mark.parametrize("name", ["c2", "c3"])
 def test_tensor_core_pipeline_parity(slam_ext, dev, name, monkeypatch):
-    """VIPE_BA_LIN3=2 routes the full linearisation of frames with <= 10 edges through the tcgen05 / TMEM pipeline
-    (ba_lin3.cu: TMA stages, TF32 hi/lo Gram in tensor memory); same bounds as the default path.  At C3 the frames with
-    more edges run the FMA kernel in the same iteration, so the two kernels' partial records are mixed."""
+    """VIPE_BA_LIN4=1 routes the full linearisation through the two-kernel Blackwell pipeline of ba_lin4.cu (disparity blocks
+    first; then asynchronously fed J warps, TF32 hi/lo Schur Gram by tcgen05.mma with the accumulators in tensor memory); same
+    bounds as the default path.  C2 has frames with fewer edges than J warps (the case that needs the completion counters), C3
+    has frames on both sides of the 10-edge boundary (one MMA per K step / four)."""
     from vipe_b200 import plan as plan_mod
 
-    monkeypatch.setenv("VIPE_BA_LIN3", "2")
+    monkeypatch.setenv("VIPE_BA_LIN4", "1")
     plan_mod._CACHE.clear()
     slam_ext._LAST_PLANS.clear()
     try:

@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib"
 SO = LIB / "libvipe_ba.so"
-SOURCES = ["ba_kernels.cu", "ba_linearize2.cu", "ba_lin3.cu", "chol.cu", "ba_api.cu", "geom_ops.cu"]
+SOURCES = ["ba_kernels.cu", "ba_linearize2.cu", "ba_lin3.cu", "ba_lin4.cu", "chol.cu", "ba_api.cu", "geom_ops.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

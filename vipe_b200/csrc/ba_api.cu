@@ -52,14 +52,17 @@ struct vipe_ba_plan {
     bool packed = false;  // linearize2 (pixel-pair) kernel
     int NTm = 256, PPTm = 1, ntile_m = 0;  // motion-only tile shape (no staging buffer => always the widest)
     int k_lo = 0, k_hi = 0, dmax = 0;
-    // owned frames by linearisation kernel: the tensor-core pipeline (ba_lin3.cu) takes 1 <= degree <= kLin3MaxDeg, the rest
-    // (no edges, or more edges than its operand tile holds) stay with the frame-major FMA kernel
-    std::vector<int> flist_tc, flist_rest;
-    int dmax_rest = 0;
-    bool use_lin3 = false, use_lin3_full = false;
-    size_t off_flist_tc = 0, off_flist_rest = 0, off_lin3_items = 0, off_econst = 0, off_slot_src = 0;
+    bool use_lin3 = false;  // TMA-fed motion-only pipeline (ba_lin3.cu)
+    size_t off_econst = 0, off_slot_src = 0;
     std::vector<int> slot_src;
-    std::vector<Lin3Item> lin3_items;
+    // second-generation pipeline (ba_lin4.cu): every owned frame has 1..kLin4MaxDeg edges
+    bool use_lin4 = false;
+    int lin4_grid = 0;
+    std::vector<Lin4Item> lin4_items;
+    std::vector<Lin4Unit> lin4_units;
+    std::vector<int> lin4_cta_item, lin4_cta_unit;
+    size_t off_lin4_items = 0, off_lin4_units = 0, off_lin4_cta_item = 0, off_lin4_cta_unit = 0, off_econst2 = 0, off_sq = 0,
+           off_sqw = 0;
     int64_t n_triples = 0;
     std::vector<int64_t> kx, kk_exp;
     std::vector<int> kx32, fptr, fedge, e_jj;
@@ -466,24 +469,28 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
         delete p;
         return fail("a source frame has too many outgoing edges for the shared-memory staging buffer");
     }
+    {
+        // VIPE_BA_LIN4: "1" = the two-kernel Blackwell pipeline of ba_lin4.cu (disparity blocks first, then asynchronously
+        // fed J warps + tcgen05 Gram in tensor memory) whenever every owned frame has 1..kLin4MaxDeg edges; "0" (default) = the
+        // frame-major FMA kernel, which is still the faster of the two on B200.  The pipeline works on
+        // 256-pixel chunks, so the partial layout of the whole plan follows.
+        const char *env4 = std::getenv("VIPE_BA_LIN4");
+        const int mode4 = env4 ? std::atoi(env4) : 0;
+        int dmin = 1 << 30;
+        for (int k = p->k_lo; k < p->k_hi; k++) dmin = std::min(dmin, p->fptr[k + 1] - p->fptr[k]);
+        p->use_lin4 = mode4 >= 1 && p->k_hi > p->k_lo && dmin >= 1 && p->HW % 4 == 0 && lin4_supported(p->HW, p->dmax);
+        if (p->use_lin4) {
+            p->packed = true;
+            p->NT = kLin4ItemPx / 2;
+            p->PPT = 2;
+        }
+    }
     p->ntile = (p->HW + p->NT * p->PPT - 1) / (p->NT * p->PPT);
     {
-        // VIPE_BA_LIN3: "0" = frame-major FMA kernels only; "1" (default) = the TMA-fed motion-only pipeline; "2" = also the
-        // tensor-core pipeline for the full linearisation of frames with <= kLin3MaxDeg edges (parity-tested, but measured no
-        // faster than the FMA kernel on B200: both run at ~0.106 us per edge at C3)
+        // VIPE_BA_LIN3: "0" = frame-major FMA kernels only; "1" (default) = the TMA-fed pipeline for motion-only runs
         const char *env = std::getenv("VIPE_BA_LIN3");
         const int mode = env ? std::atoi(env) : 1;
         p->use_lin3 = mode >= 1 && p->packed && lin3_supported(p->HW, p->NT * p->PPT);
-        p->use_lin3_full = p->use_lin3 && mode >= 2;
-        for (int k = p->k_lo; k < p->k_hi; k++) {
-            const int d = p->fptr[k + 1] - p->fptr[k];
-            if (p->use_lin3_full && d >= 1 && d <= kLin3MaxDeg) {
-                p->flist_tc.push_back(k);
-            } else {
-                p->flist_rest.push_back(k);
-                p->dmax_rest = std::max(p->dmax_rest, d);
-            }
-        }
     }
     // motion-only shares the partial layout (ntile), so it uses the same tile shape
     p->NTm = p->NT;
@@ -522,24 +529,50 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     p->off_pn = take(sizeof(int) * C);
     p->off_prow0 = take(sizeof(int) * C);
     p->off_pn_focal = take(sizeof(int) * C);
-    {
-        const int chunk_px = p->NT * p->PPT, nchunk = chunk_px > 0 ? p->HW / chunk_px : 0;
-        for (int k : p->flist_tc)
+    if (p->use_lin4) {
+        // items: frames by descending degree (the contiguous CTA ranges below then hold items of similar cost), chunk-major inside
+        std::vector<int> order;
+        for (int k = p->k_lo; k < p->k_hi; k++) order.push_back(k);
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return p->fptr[x + 1] - p->fptr[x] > p->fptr[y + 1] - p->fptr[y]; });
+        const int nchunk = p->HW / kLin4ItemPx, nsub = kLin4ItemPx / 64;
+        std::vector<long long> ucum(1, 0);
+        for (int k : order) {
+            const int s0 = p->fptr[k], d = p->fptr[k + 1] - s0, src = p->kx32[k];
             for (int ch = 0; ch < nchunk; ch++) {
-                Lin3Item it;
-                it.k = k, it.src = p->kx32[k], it.s0 = p->fptr[k], it.d = p->fptr[k + 1] - p->fptr[k];
-                it.px0 = ch * chunk_px, it.chunk = ch;
-                for (int m = 0; m < kLin3MaxDeg; m++) it.edge[m] = m < it.d ? p->fedge[it.s0 + m] : -1;
-                p->lin3_items.push_back(it);
+                const int item = (int)p->lin4_items.size();
+                p->lin4_items.push_back(Lin4Item{k, d, ch, 0});
+                for (int t = 0; t < nsub; t++)
+                    for (int e = 0; e < d; e++) {
+                        const int px0 = ch * kLin4ItemPx + t * 64;
+                        p->lin4_units.push_back(Lin4Unit{s0 + e, p->fedge[s0 + e], src * p->HW + px0, k * p->HW + px0, e | (d << 8),
+                                                          ((px0 / p->wd) << 16) | (px0 % p->wd), px0, item * nsub + t});
+                    }
+                ucum.push_back((long long)p->lin4_units.size());
             }
+        }
+        const int nitems = (int)p->lin4_items.size();
+        p->lin4_grid = std::min(device_sm_count(), nitems);
+        const long long total_units = ucum.back();
+        p->lin4_cta_item.assign(p->lin4_grid + 1, 0);
+        p->lin4_cta_unit.assign(p->lin4_grid + 1, 0);
+        int it = 0;
+        for (int b = 1; b <= p->lin4_grid; b++) {
+            const long long target = total_units * b / p->lin4_grid;
+            const int lo = it;  // at least one item per CTA, and enough left for the CTAs behind
+            while (it < nitems - (p->lin4_grid - b) && (it == lo || ucum[it + 1] <= target)) it++;
+            if (b == p->lin4_grid) it = nitems;
+            p->lin4_cta_item[b] = it;
+            p->lin4_cta_unit[b] = (int)ucum[it];
+        }
     }
-    p->off_lin3_items = take(sizeof(Lin3Item) * std::max<size_t>(p->lin3_items.size(), 1));
+    p->off_lin4_items = take(sizeof(Lin4Item) * std::max<size_t>(p->lin4_items.size(), 1));
+    p->off_lin4_units = take(sizeof(Lin4Unit) * std::max<size_t>(p->lin4_units.size(), 1));
+    p->off_lin4_cta_item = take(sizeof(int) * std::max<size_t>(p->lin4_cta_item.size(), 1));
+    p->off_lin4_cta_unit = take(sizeof(int) * std::max<size_t>(p->lin4_cta_unit.size(), 1));
     p->slot_src.assign(std::max<int64_t>(E, 1), 0);
     for (int k = 0; k < K; k++)
         for (int s2 = p->fptr[k]; s2 < p->fptr[k + 1]; s2++) p->slot_src[s2] = p->kx32[k];
     p->off_slot_src = take(sizeof(int) * p->slot_src.size());
-    p->off_flist_tc = take(sizeof(int) * std::max<size_t>(p->flist_tc.size(), 1));
-    p->off_flist_rest = take(sizeof(int) * std::max<size_t>(p->flist_rest.size(), 1));
     p->off_psys = take(sizeof(int) * n_frames);
     p->off_cbase = take(sizeof(long long) * (K + 1));
     p->off_vbase = take(sizeof(long long) * (K + 1));
@@ -559,7 +592,10 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     p->off_fpart = take(sizeof(float) * (size_t)std::max<int64_t>(E, 1) * p->ntile_f * kFocalStride);
     p->off_ffpart = take(sizeof(float) * (size_t)K * p->ntile_f * 2);
     p->off_uf = take(sizeof(float) * (size_t)K * p->HW);
-    p->off_epart = take(sizeof(float) * (size_t)std::max<int64_t>(E, 1) * p->ntile * kEdgeStride);
+    p->off_econst2 = take(sizeof(float) * 32 * (p->use_lin4 ? (size_t)std::max<int64_t>(E, 1) : 1));
+    p->off_sq = take(sizeof(float) * (p->use_lin4 ? (size_t)K * p->HW : 1));
+    p->off_sqw = take(sizeof(float) * (p->use_lin4 ? (size_t)K * p->HW : 1));
+    p->off_epart = take(sizeof(float) * (size_t)std::max<int64_t>(E, 1) * (p->use_lin4 ? std::max(p->ntile, p->HW / 64) : p->ntile) * kEdgeStride);
     p->off_gpart = take(sizeof(float) * (size_t)std::max<long long>(p->gbase[K], 1));
     p->off_msc = take(sizeof(double) * (size_t)std::max<long long>(p->mbase[K], 1));
     p->off_q = take(sizeof(float) * (size_t)K * p->HW);
@@ -608,11 +644,10 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     std::memcpy(p->blob.data() + p->off_rowmap, p->rowmap.data(), sizeof(int) * p->npad);
     if (!p->tstruct.empty()) std::memcpy(p->blob.data() + p->off_tstruct, p->tstruct.data(), p->tstruct.size());
     std::memcpy(p->blob.data() + p->off_slot_src, p->slot_src.data(), sizeof(int) * p->slot_src.size());
-    if (!p->lin3_items.empty())
-        std::memcpy(p->blob.data() + p->off_lin3_items, p->lin3_items.data(), sizeof(Lin3Item) * p->lin3_items.size());
-    if (!p->flist_tc.empty()) std::memcpy(p->blob.data() + p->off_flist_tc, p->flist_tc.data(), sizeof(int) * p->flist_tc.size());
-    if (!p->flist_rest.empty())
-        std::memcpy(p->blob.data() + p->off_flist_rest, p->flist_rest.data(), sizeof(int) * p->flist_rest.size());
+    put(p->off_lin4_items, p->lin4_items.data(), sizeof(Lin4Item) * p->lin4_items.size());
+    put(p->off_lin4_units, p->lin4_units.data(), sizeof(Lin4Unit) * p->lin4_units.size());
+    put(p->off_lin4_cta_item, p->lin4_cta_item.data(), sizeof(int) * p->lin4_cta_item.size());
+    put(p->off_lin4_cta_unit, p->lin4_cta_unit.data(), sizeof(int) * p->lin4_cta_unit.size());
     {
         std::vector<int> nf(p->prob_n);
         for (auto &v : nf) v += 1;
@@ -703,6 +738,7 @@ static Tables make_tables(const vipe_ba_plan *p, void *ws) {
     tb.prob_row0 = (const int *)(w + p->off_prow0);
     tb.C = p->C;
     tb.ntile = p->ntile;
+    tb.ntile_e = p->ntile;
     tb.k_lo = p->k_lo;
     tb.k_hi = p->k_hi;
     tb.rows_by_slot = p->rows_by_slot;
@@ -765,19 +801,24 @@ static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void 
     la.gpart = (float *)(w + p->off_gpart);
     la.qbuf = (float *)(w + p->off_q);
     la.qwbuf = (float *)(w + p->off_qw);
-    if (p->packed && !motion_only && p->use_lin3_full) {
-        // two launches over disjoint frame lists: tensor-core pipeline for the low-degree frames, FMA kernel for the rest
-        if (!p->flist_tc.empty()) {
-            VBA_CUDA(launch_lin3(la, (const Lin3Item *)(w + p->off_lin3_items), (int)p->flist_tc.size(), p->NT * p->PPT,
-                                 (float *)(w + p->off_econst), device_sm_count(), st));
-            p->launches += 2;
-        }
-        if (!p->flist_rest.empty()) {
-            la.flist = (const int *)(w + p->off_flist_rest);
-            VBA_CUDA(launch_linearize2(la, (int)p->flist_rest.size(), std::max(p->dmax_rest, 1), false, p->NT, st));
-            la.flist = nullptr;
-            p->launches++;
-        }
+    if (p->use_lin4 && !motion_only) {
+        la.tb.ntile_e = p->HW / 64;  // one edge record per 64-pixel unit
+        Lin4Launch l4;
+        l4.items = (const Lin4Item *)(w + p->off_lin4_items);
+        l4.units = (const Lin4Unit *)(w + p->off_lin4_units);
+        l4.cta_item = (const int *)(w + p->off_lin4_cta_item);
+        l4.cta_unit = (const int *)(w + p->off_lin4_cta_unit);
+        l4.grid = p->lin4_grid;
+        l4.nframes = nframes;
+        l4.dmax = std::max(p->dmax, 1);
+        l4.slot_src = (const int *)(w + p->off_slot_src);
+        l4.slot_lo = p->fptr[p->k_lo];
+        l4.nslots = p->fptr[p->k_hi] - l4.slot_lo;
+        l4.econst2 = (float2 *)(w + p->off_econst2);
+        l4.sqbuf = (float *)(w + p->off_sq);
+        l4.sqwbuf = (float *)(w + p->off_sqw);
+        VBA_CUDA(launch_lin4(la, l4, st));
+        p->launches += 3;
     } else if (p->packed && motion_only && p->use_lin3) {
         const int slot_lo = p->fptr[p->k_lo], nslots = p->fptr[p->k_hi] - slot_lo;
         VBA_CUDA(launch_lin3_motion(la, (const int *)(w + p->off_slot_src), slot_lo, nslots, p->NT * p->PPT, (float *)(w + p->off_econst),

@@ -33,6 +33,7 @@ struct Tables {
     const int *prob_n;           // [C] system size 6 * (free poses)
     const int *prob_row0;        // [C] first dx row of the problem
     int K, E, N, HW, wd, ntile, k_lo, k_hi, C;
+    int ntile_e = 0;  // partial records per edge slot in epart (= ntile, except behind ba_lin4.cu: one per 64-pixel unit)
     // owner-only pixel inputs (multi-GPU): targets/weights hold just the rows of this rank's edges, in CSR slot order
     int rows_by_slot = 0, slot_lo = 0;
 };

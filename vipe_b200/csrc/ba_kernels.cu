@@ -384,8 +384,8 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
     }
     for (int idx = tid; idx < d * kEdgeVals; idx += NT) {
         const int m = idx / kEdgeVals, r = idx - m * kEdgeVals;
-        const float *ep = a.epart + ((size_t)(s0 + m) * ntile) * kEdgeStride + r;
-        hs[idx] = tile_sum(ep, kEdgeStride, ntile);
+        const float *ep = a.epart + ((size_t)(s0 + m) * tb.ntile_e) * kEdgeStride + r;
+        hs[idx] = tile_sum(ep, kEdgeStride, tb.ntile_e);
     }
     __syncthreads();
 

@@ -14,20 +14,38 @@ cudaError_t launch_linearize(const LinArgs &a, int nframes, int dmax, bool motio
 // packed 2-pixels-per-thread variant (ba_linearize2.cu); needs an even HW.  TILE = 2 * NT.
 bool tile_config2(int HW, int dmax, bool motion, int &NT);
 cudaError_t launch_linearize2(const LinArgs &a, int nframes, int dmax, bool motion, int NT, cudaStream_t st);
-// Blackwell pipeline (ba_lin3.cu): TMA stages + tcgen05 Gram for frames with 1 <= out-degree <= kLin3MaxDeg.  The plan lists
-// its work as items (frame, chunk of `chunk_px` pixels = one partial record), frame-major; `econst_dev` is E x 16 floats of
-// scratch for the per-edge constants.
-constexpr int kLin3MaxDeg = 10;
-struct Lin3Item {
-    int k, src, s0, d, px0, chunk;  // kx position, frame id, first edge slot, out-degree, first pixel, chunk index
-    int edge[kLin3MaxDeg];          // edge ids, -1 beyond d
-};
+// TMA-fed motion-only pipeline (ba_lin3.cu); `econst_dev` is E x 16 floats of scratch for the per-edge constants.
 bool lin3_supported(int HW, int chunk_px);
-cudaError_t launch_lin3(const LinArgs &a, const Lin3Item *items_dev, int nframes, int chunk_px, float *econst_dev, int num_sms,
-                        cudaStream_t st);
 // motion-only variant: flat (edge slot, chunk) units over the slots [slot_lo, slot_lo + nslots); `slot_src_dev[slot]` = source frame id
 cudaError_t launch_lin3_motion(const LinArgs &a, const int *slot_src_dev, int slot_lo, int nslots, int chunk_px, float *econst_dev,
                                int num_sms, cudaStream_t st);
+// Second-generation pipeline (ba_lin4.cu): cw_kernel (disparity blocks -> Q) + lin4_kernel (TMA-fed J warps, tcgen05 Gram) for
+// frames with 1 <= out-degree <= kLin4MaxDeg.  Items = (frame, 256-pixel chunk), units = (item, 64-pixel sub-tile, edge) in that
+// order; CTA b of the persistent grid owns the contiguous item range [cta_item[b], cta_item[b + 1]) and its units
+// [cta_unit[b], cta_unit[b + 1]).  epart holds one record per unit (Tables::ntile_e = HW / 64).
+constexpr int kLin4MaxDeg = 20, kLin4GroupDeg = 10, kLin4NJ = 10, kLin4ItemPx = 256;
+struct Lin4Item {
+    int k, d, chunk, pad;  // kx position, out-degree, chunk index
+};
+struct Lin4Unit {
+    int slot, edge;  // CSR slot and edge id
+    int srcpx, kpx;  // src * HW + px0, k * HW + px0
+    int ed;          // position of the edge in its frame | out-degree of the frame << 8
+    int rc;          // image row of px0 << 16 | column of px0
+    int px0, g;      // first pixel inside the frame; running sub-tile number (item * 4 + sub-tile) in list order
+};
+struct Lin4Launch {
+    const Lin4Item *items;
+    const Lin4Unit *units;
+    const int *cta_item, *cta_unit;  // [grid + 1]
+    int grid, nframes, dmax;
+    const int *slot_src;
+    int slot_lo, nslots;
+    float2 *econst2;         // [E][16] per-edge constants, each value twice
+    float *sqbuf, *sqwbuf;   // [K][HW] sqrt(Q), sqrt(Q) w
+};
+bool lin4_supported(int HW, int dmax);
+cudaError_t launch_lin4(const LinArgs &a, const Lin4Launch &l, cudaStream_t st);
 cudaError_t launch_frame_reduce(const ReduceArgs &a, int nframes, int dmax, cudaStream_t st);
 cudaError_t launch_assemble(const AssembleArgs &a, cudaStream_t st);
 cudaError_t launch_backsub(const BackArgs &a, int nframes, int dmax, cudaStream_t st);

@@ -38,28 +38,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     return ok != 0;
 }
 // A wait that can never complete (a pipeline bug) must not hang the GPU: after ~4 s it reports and traps.
-__device__ __noinline__ void mbar_timeout(uint64_t *bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_timeout(uint64_t *bar, uint32_t parity) {
     printf("mbarrier wait timed out: block %d thread %d bar@%u parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
     __trap();
 }
+// The polling loops are kept to a handful of instructions (they compete for issue slots with the warps doing the work); a
+// wait that can never complete traps after ~2^26 polls instead of reading the clock on every poll.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 1023u) == 0 && clock64() - t0 > 8000000000LL) mbar_timeout(bar, parity);
+        if (++spins > (1u << 26)) mbar_timeout(bar, parity);
     }
 }
 
-// for roles that expect to wait long (producer, MMA issuer, flush warps): back off between polls so that the polling
-// does not take issue slots and shared-memory-pipe bandwidth from the warps doing the work
+// for roles that expect to wait long (MMA issuer, flush warps): back off between polls
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(200);
-        if ((++spins & 255u) == 0 && clock64() - t0 > 8000000000LL) mbar_timeout(bar, parity);
+        __nanosleep(100);
+        if (++spins > (1u << 24)) mbar_timeout(bar, parity);
     }
 }
 

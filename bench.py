@@ -362,7 +362,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side", action="store_true", help="skip the C4 / C5 / C2 side measurements")
-    ap.add_argument("--collective", default="auto", choices=["auto", "nvls", "nvls2", "allreduce"],
+    ap.add_argument("--collective", default="auto", choices=["auto", "nvls", "nvls2", "dist", "allreduce"],
                     help="N > 1: how the ranks' partial reduced systems are summed (vipe_b200/distributed.py)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)

@@ -175,6 +175,22 @@ int vipe_ba_peer_reduce(const vipe_ba_plan *plan, const double *accum_multicast,
                         void *stream);
 int vipe_ba_set_solve_buffer(vipe_ba_plan *plan, double *reduced_local);
 /*
+ * Distributed factorisation (one process per GPU, NVSwitch multicast memory): instead of every rank factorising the whole
+ * reduced system, tile column j of the 64 x 64 tile grid belongs to rank j % world.  An owner reads its input tiles summed
+ * over the ranks' partial systems (the multicast address given to vipe_ba_set_peer_system -- required), factorises, and
+ * writes L, y = L^-1 b and the inverted diagonal tiles through the MULTICAST aliases, so they land in every rank's instance
+ * together with the tile's ready flag; consumers wait on their local flags and read local memory.  The backward
+ * substitution is replicated, so every rank ends with the same dx.  `factor_*`: symmetric buffer of n*n + 2n doubles
+ * (vipe_ba_system_buffer's count), `aux_*`: symmetric buffer of vipe_ba_dist_aux_bytes(plan) bytes, zero-filled once when it
+ * is created and never touched by the caller afterwards (its ready flags carry a per-solve epoch instead of being reset).
+ * One cross-rank barrier per iteration, between vipe_ba_linearize and vipe_ba_solve_update, as with the fused loads; the
+ * accumulation buffers alternate in the same way.  Replaces the reference's single-GPU SimplicialLLT solve
+ * (csrc/slam_ext/geom_kernels.cu:1172-1191).  NULL factor_local: off.
+ */
+int64_t vipe_ba_dist_aux_bytes(const vipe_ba_plan *plan);
+int vipe_ba_set_dist_solve(vipe_ba_plan *plan, double *factor_local, double *factor_multicast, void *aux_local,
+                           void *aux_multicast, int rank, int world);
+/*
  * Owner-only pixel inputs for sharded plans (a rank HOLDS the targets/weights of its edges): when
  * on, `targets` / `weights` in vipe_ba_tensors are [n_owned, 2, ht, wd], the rows of this rank's edges in the order of
  * vipe_ba_plan_copy_owned_edges (the plan's CSR order over the owned source frames).  Everything else stays replicated.

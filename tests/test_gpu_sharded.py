@@ -52,7 +52,7 @@ def _free_port():
 
 
 @pytest.mark.parametrize("name,collective,owned", [("c2", "allreduce", False), ("c3", "allreduce", True), ("c3", "nvls", False),
-                                                   ("c3", "nvls2", True)])
+                                                   ("c3", "nvls2", True), ("c3", "dist", True)])
 def test_sharded_matches_single_gpu(lib_built, tmp_path, name, collective, owned):
     """"nvls": no all-reduce launch; the Cholesky kernel reads the sum of the ranks' partial systems through the NVSwitch
     (multimem.ld_reduce), see vipe_b200/distributed.py PeerSystem.  "nvls2": the in-switch sum as a reduce-scatter +

@@ -71,6 +71,8 @@ SIGNATURES = {
     "vipe_ba_plan_copy_owned_edges": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vipe_ba_set_owned_rows": (C.c_int, [C.c_void_p, C.c_int]),
     "vipe_ba_set_solve_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vipe_ba_dist_aux_bytes": (C.c_int64, [C.c_void_p]),
+    "vipe_ba_set_dist_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "vipe_ba_peer_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "vipe_ba_plan_max_degree": (C.c_int, [C.c_void_p]),
     "vipe_ba_workspace_bytes": (C.c_size_t, [C.c_void_p]),

@@ -117,6 +117,11 @@ struct vipe_ba_plan {
     mutable double *solve_buf = nullptr;  // where solve_update reads and factorises the system (null: the workspace)
     mutable int rows_by_slot = 0;         // targets/weights hold only this rank's edges, in CSR slot order
     mutable const double *peer_mc = nullptr;
+    // distributed factorisation (vipe_ba_set_dist_solve): this rank's instances and the multicast aliases of the factor
+    // buffer [L ; y] and of the solver's auxiliary buffer [scratch ints ; 1/diag ; L_jj^-T tiles]
+    mutable double *dist_factor = nullptr, *dist_factor_mc = nullptr;
+    mutable unsigned char *dist_aux = nullptr, *dist_aux_mc = nullptr;
+    mutable int dist_rank = 0, dist_world = 1, dist_epoch = 0;
     // optional stage timing
     bool profile = false;
     mutable std::vector<cudaEvent_t> events;  // 5 per iteration
@@ -777,6 +782,14 @@ static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void 
     if (check_tensors(p, t, motion_only)) return 1;
     if (!ws) return fail("null workspace");
     unsigned char *w = (unsigned char *)ws;
+    if (p->dist_factor) {
+        // Distributed solve: what the owners multicast validates itself against ZERO words, so this rank's receiving copies
+        // ([L ; y] and the L_jj^-T tiles) are cleared here -- before the cross-rank barrier that precedes the solve, so that no
+        // rank can be writing into them yet, and after this rank's own reads of the previous solve (stream order).
+        const size_t soff = align_up(chol_scratch_ints(p->npad) * sizeof(int));
+        VBA_CUDA(cudaMemsetAsync(p->dist_factor, 0, sizeof(double) * ((size_t)p->npad * p->npad + p->npad), st));
+        VBA_CUDA(cudaMemsetAsync(p->dist_aux + soff + sizeof(double) * p->npad, 0, sizeof(double) * (size_t)p->npad * kCholBlock, st));
+    }
     double *H = p->peer_accum ? p->peer_accum : (double *)(w + p->off_sys);
     {
         const Tables t0b = make_tables(p, ws);
@@ -905,9 +918,29 @@ static int solve_update_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, vo
     if (!ws) return fail("null workspace");
     if (p->P <= 0) return 0;
     unsigned char *w = (unsigned char *)ws;
-    double *H = p->solve_buf ? p->solve_buf : (double *)(w + p->off_sys);
+    double *H = p->dist_factor ? p->dist_factor : p->solve_buf ? p->solve_buf : (double *)(w + p->off_sys);
     double *b = H + (size_t)p->npad * p->npad;
     int *scratch = (int *)(w + p->off_flag);
+    double *dinv = (double *)(w + p->off_dx);
+    CholDist cd;
+    const CholDist *dist = nullptr;
+    if (p->dist_factor) {
+        if (!p->peer_mc) return fail("the distributed solve reads its input through vipe_ba_set_peer_system's multicast address");
+        if (p->opt.optimize_focal) return fail("optimize_focal is not supported with the distributed solve");
+        const size_t soff = align_up(chol_scratch_ints(p->npad) * sizeof(int));
+        scratch = (int *)p->dist_aux;
+        dinv = (double *)(p->dist_aux + soff);
+        cd.rank = p->dist_rank, cd.world = p->dist_world, cd.epoch = ++p->dist_epoch;
+        {
+            const char *env = std::getenv("VIPE_BA_DIST_COLBLK");
+            // blocks of two columns from 4 GPUs on (measured at C4: 207 vs 210 it/s on 2 GPUs, 300 vs 296 on 8)
+            cd.colblk = env ? std::max(1, std::atoi(env)) : (p->dist_world >= 4 ? 2 : 1);
+        }
+        cd.Hmc = p->dist_factor_mc;
+        cd.scratch_mc = (int *)p->dist_aux_mc;
+        cd.linvT_mc = (double *)(p->dist_aux_mc + soff) + p->npad;
+        dist = &cd;
+    }
     int cnt = 0;
     p->epoch++;
     const Tables tbs = make_tables(p, ws);
@@ -918,10 +951,10 @@ static int solve_update_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, vo
         if (focal) VBA_CUDA(launch_add_scalar(H + (size_t)p->n * p->npad + p->n, (double)p->opt.focal_ep - (double)ep, st));
         if ((p->peer_mc || p->solve_buf) && p->npad <= 2 * kCholBlock)
             return fail("the fused multi-GPU reduction needs the tiled solver (more than 128 unknowns); use the all-reduce path");
-        VBA_CUDA(launch_damped_solve(H, b, p->n + (focal ? 1 : 0), p->npad, lm, ep, t->dx_out, scratch, (double *)(w + p->off_dx),
-                                     (double *)(w + p->off_dx) + p->npad, p->opt.damp_on_pose_hessian ? b + p->npad : nullptr,
-                                     p->solve_buf ? nullptr : p->peer_mc, p->epoch, p->ordered ? (const unsigned char *)(w + p->off_tstruct) : nullptr,
-                                     nullptr, st, &cnt));
+        VBA_CUDA(launch_damped_solve(H, b, p->n + (focal ? 1 : 0), p->npad, lm, ep, t->dx_out, scratch, dinv, dinv + p->npad,
+                                     p->opt.damp_on_pose_hessian ? b + p->npad : nullptr,
+                                     (p->solve_buf && !dist) ? nullptr : p->peer_mc, p->epoch,
+                                     p->ordered ? (const unsigned char *)(w + p->off_tstruct) : nullptr, nullptr, st, &cnt, dist));
     } else {  // many small independent problems: one CTA each
         VBA_CUDA(launch_small_solve_batch(H, tbs.prob_hoff, tbs.prob_n, tbs.prob_npad, tbs.prob_row0, p->C, lm, ep, t->dx_out,
                                           p->opt.damp_on_pose_hessian != 0, st, &cnt));
@@ -1019,6 +1052,26 @@ extern "C" int vipe_ba_set_peer_system(vipe_ba_plan *p, double *accum_local, con
     return 0;
 }
 
+extern "C" int64_t vipe_ba_dist_aux_bytes(const vipe_ba_plan *p) {
+    if (!p) return -1;
+    return (int64_t)(align_up(chol_scratch_ints(p->npad) * sizeof(int)) + sizeof(double) * ((size_t)p->npad + (size_t)p->npad * kCholBlock));
+}
+extern "C" int vipe_ba_set_dist_solve(vipe_ba_plan *p, double *factor_local, double *factor_multicast, void *aux_local,
+                                      void *aux_multicast, int rank, int world) {
+    if (!p) return fail("null plan");
+    if (factor_local && (!factor_multicast || !aux_local || !aux_multicast || world < 2 || rank < 0 || rank >= world))
+        return fail("vipe_ba_set_dist_solve: all four buffers and 0 <= rank < world >= 2 are needed");
+    if (factor_local && (p->C != 1 || p->npad <= 2 * kCholBlock)) return fail("the distributed solve needs one problem with more than 128 unknowns");
+    p->dist_factor = factor_local;
+    p->dist_factor_mc = factor_multicast;
+    p->dist_aux = (unsigned char *)aux_local;
+    p->dist_aux_mc = (unsigned char *)aux_multicast;
+    p->dist_rank = rank, p->dist_world = world;
+    for (auto &g : p->graphs)  // captured runs hold the old routing
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    p->graphs.clear();
+    return 0;
+}
 extern "C" int vipe_ba_set_solve_buffer(vipe_ba_plan *p, double *local) {
     if (!p) return fail("null plan");
     if (local && p->C != 1) return fail("batched plans are not sharded");

@@ -57,6 +57,18 @@ int focal_tiles(int HW);
 cudaError_t launch_add_scalar(double *p, double v, cudaStream_t st);
 cudaError_t launch_focal(const FocalArgs &a, int nframes, int dmax, cudaStream_t st);
 
+// Distributed factorisation over `world` GPUs (tile columns cyclic over the ranks, results multicast through the NVSwitch):
+// H / scratch / linvT passed to launch_damped_solve are this rank's instances of symmetric buffers, the fields below their
+// multicast aliases; Ain (the multicast address of the ranks' partial systems) is required; `epoch` must be the same on every
+// rank and different from the previous solve's.
+struct CholDist {
+    int rank, world, epoch;
+    int colblk;  // tile columns are dealt to the ranks in blocks of this many (neighbouring columns on one rank keep the
+                 // single-GPU shortcuts of the column-to-column hand-over; 1 = plain cyclic)
+    double *Hmc;
+    int *scratch_mc;
+    double *linvT_mc;
+};
 // Dense damped Cholesky solve of the reduced camera system (chol.cu).
 //   H: [npad x npad] fp64 row-major, lower triangle valid on entry (destroyed);  b: [npad] fp64 (destroyed)
 //   diag += ep + lm*diag (geom_kernels.cu:1176); factor; solve; dx[n] fp32.  Failure => dx = 0 (:1186-1188).
@@ -70,7 +82,7 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
                                 const double *Ain /*null, or multicast address of the ranks' [H;b;diag(A)] partials*/,
                                 int epoch, const unsigned char *tstruct /*DEV [T][T] tile structure of L, or null = dense*/,
                                 const int *rowmap /*DEV [npad] system unknown -> dx index, or null = identity*/, cudaStream_t st,
-                                int *launches);
+                                int *launches, const CholDist *dist = nullptr);
 size_t chol_scratch_ints(int npad);
 // Two-step in-switch all-reduce of the ranks' partial systems [H (lower tiles) ; b ; diag(A)]: this rank sums every world-th
 // tile over all instances (multimem.ld_reduce through `accum_mc`) and multicasts the sums into every rank's instance of

@@ -17,6 +17,10 @@
 // A non-positive (or NaN) pivot raises *fail and the solve writes dx = 0, like the reference (:1186-1188).
 #include <type_traits>
 
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 #include "ba_launch.h"
 
 namespace vba {
@@ -54,12 +58,43 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
 __device__ __forceinline__ void st_release(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {  // (a hint in the distributed solve: relaxed is enough)
+    int v;
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// `dist`: the flag may have been set by another GPU (distributed factorisation): system-scope acquire
+__device__ __forceinline__ bool flag_is(const int *f, int epoch, bool dist) { return (dist ? ld_acquire_sys(f) : ld_acquire(f)) == epoch; }
 // all threads call; returns after flag == epoch is visible to the whole CTA
-__device__ __forceinline__ void wait_flag(const int *f, int epoch) {
+__device__ __forceinline__ void wait_flag(const int *f, int epoch, bool dist = false) {
     if (threadIdx.x == 0) {
-        while (ld_acquire(f) != epoch) __nanosleep(32);
+        while (!flag_is(f, epoch, dist)) __nanosleep(32);
     }
     __syncthreads();
+}
+// ---- distributed factorisation: results go to every rank's instance through the NVSwitch multicast address --------------
+__device__ __forceinline__ bool is_hole(double x) { return __double_as_longlong(x) == 0ll; }
+__device__ __forceinline__ void mc_store(double *p, double v) {
+    if (is_hole(v)) v = -0.0;
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+// Everything an owner multicasts is SELF-VALIDATING: the receiving buffers are zeroed before the solve, every 8-byte word that
+// travels has a non-zero bit pattern (+0.0 goes as -0.0), and a reader re-fetches until it sees no zero word.  The ready flags
+// are then mere hints, stored relaxed right behind the data: no fence, no release.  (A system-scope release behind 32 KB of
+// multicast stores was measured at ~10 us per tile -- on the critical path of every tile column.)
+// two adjacent doubles in one 16-byte multicast store (multimem.st has no f64 vector form; the bits travel as 4 x f32)
+__device__ __forceinline__ void mc_store2(double *p, double x, double y) {
+    unsigned long long bx = (unsigned long long)__double_as_longlong(x), by = (unsigned long long)__double_as_longlong(y);
+    if (bx == 0ull) bx = 0x8000000000000000ull;
+    if (by == 0ull) by = 0x8000000000000000ull;
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float((unsigned)bx)),
+                 "f"(__uint_as_float((unsigned)(bx >> 32))), "f"(__uint_as_float((unsigned)by)), "f"(__uint_as_float((unsigned)(by >> 32)))
+                 : "memory");
+}
+// all threads call after their multicast writes: the flag lands in every rank's flag array behind the data
+__device__ __forceinline__ void publish_flag_mc(int *f_mc, int epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("multimem.st.relaxed.sys.global.b32 [%0], %1;" ::"l"(f_mc), "r"(epoch) : "memory");
 }
 // all threads call after their global writes
 __device__ __forceinline__ void publish_flag(int *f, int epoch) {
@@ -112,7 +147,17 @@ struct CholArgs {
     // index in dx (undoes that order).
     const unsigned char *ts;
     const int *rowmap;
+    // Distributed factorisation (world > 1): tile column j (and its rhs tile) belongs to rank j % world.  Every rank holds a
+    // full copy of L, y, L_jj^-T and the ready flags in symmetric memory; an owner writes its results through the multicast
+    // aliases below, so they land in every rank's copy, and consumers wait on their LOCAL flags and read LOCAL memory.  The
+    // input is summed over the ranks' partial systems by the owner's loads (Ain).  Flags hold the solve's epoch (no reset
+    // between solves: a reset could race with a faster rank's publications).  The backward substitution is replicated.
+    int rank = 0, world = 1, colblk = 1;  // columns are dealt in blocks of `colblk`: owner(j) = (j / colblk) % world
+    double *Hmc = nullptr, *bmc = nullptr, *linvT_mc = nullptr;
+    int *flags_mc = nullptr, *fail_mc = nullptr;
+    int *lflags = nullptr, *lflags_mc = nullptr;  // [T] L_jj^-T of column j has arrived (the backward substitution reads it)
 };
+__device__ __forceinline__ int col_owner(const CholArgs &a, int j) { return (j / a.colblk) % a.world; }
 
 // one element of the rank-summed input system through the switch (NVLS in-switch reduction)
 __device__ __forceinline__ double mc_load_sum(const double *p) {
@@ -272,6 +317,66 @@ __device__ __forceinline__ void load_tile_T(double *S, const double *__restrict_
         const int idx = threadIdx.x + u * CT;
         const int r = idx >> 5, k2 = (idx & 31) * 2;
         v[u] = __ldcg(reinterpret_cast<const double2 *>(G + (size_t)r * ld + k2));
+    }
+#pragma unroll
+    for (int u = 0; u < TB * TB / 2 / CT; u++) {
+        const int idx = threadIdx.x + u * CT;
+        const int r = idx >> 5, k2 = (idx & 31) * 2;
+        S[k2 * LD + r] = v[u].x;
+        S[(k2 + 1) * LD + r] = v[u].y;
+    }
+}
+
+// Self-validating variants for the distributed solve (see mc_store2): every thread re-fetches its own 16-byte pieces until
+// they hold no zero word.  fix_holes repairs what tile_cp_async left in shared memory (same thread -> element mapping).
+__device__ __forceinline__ void load_tile_R_valid(double *S, const double *__restrict__ G, int ld) {
+    double2 v[TB * TB / 2 / CT];
+    for (;;) {
+        bool bad = false;
+#pragma unroll
+        for (int u = 0; u < TB * TB / 2 / CT; u++) {
+            const int idx = threadIdx.x + u * CT;
+            v[u] = __ldcg(reinterpret_cast<const double2 *>(G + (size_t)(idx >> 5) * ld + (idx & 31) * 2));
+        }
+#pragma unroll
+        for (int u = 0; u < TB * TB / 2 / CT; u++) bad |= is_hole(v[u].x) | is_hole(v[u].y);
+        if (!bad) break;
+        __nanosleep(100);
+    }
+#pragma unroll
+    for (int u = 0; u < TB * TB / 2 / CT; u++) {
+        const int idx = threadIdx.x + u * CT;
+        *reinterpret_cast<double2 *>(S + (idx >> 5) * RS + (idx & 31) * 2) = v[u];
+    }
+}
+__device__ __forceinline__ void fix_holes(double *S, const double *__restrict__ G, int ld) {
+#pragma unroll
+    for (int u = 0; u < TB * TB / 2 / CT; u++) {
+        const int idx = threadIdx.x + u * CT;
+        const int r = idx >> 5, k2 = (idx & 31) * 2;
+        double2 v = *reinterpret_cast<const double2 *>(S + r * RS + k2);
+        if (is_hole(v.x) | is_hole(v.y)) {
+            do {
+                __nanosleep(100);
+                v = __ldcg(reinterpret_cast<const double2 *>(G + (size_t)r * ld + k2));
+            } while (is_hole(v.x) | is_hole(v.y));
+            *reinterpret_cast<double2 *>(S + r * RS + k2) = v;
+        }
+    }
+}
+__device__ __forceinline__ void load_tile_T_valid(double *S, const double *__restrict__ G, int ld) {
+    double2 v[TB * TB / 2 / CT];
+    for (;;) {
+        bool bad = false;
+#pragma unroll
+        for (int u = 0; u < TB * TB / 2 / CT; u++) {
+            const int idx = threadIdx.x + u * CT;
+            v[u] = __ldcg(reinterpret_cast<const double2 *>(G + (size_t)(idx >> 5) * ld + (idx & 31) * 2));
+        }
+#pragma unroll
+        for (int u = 0; u < TB * TB / 2 / CT; u++) bad |= is_hole(v[u].x) | is_hole(v[u].y);
+        if (!bad) break;
+        __nanosleep(100);
     }
 #pragma unroll
     for (int u = 0; u < TB * TB / 2 / CT; u++) {
@@ -546,6 +651,7 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
     __shared__ unsigned short klist[kMaxSparseT];
     const int T = a.T, ld = a.ld, tid = threadIdx.x;
     const int total = T * (T + 1) / 2 + T;  // lower tiles + one rhs tile per column
+    const bool dist = a.world > 1;
     for (;;) {
         __syncthreads();
         if (tid == 0) {
@@ -568,6 +674,11 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
         }
         const int i = j + (t - (j * (T + 1) - j * (j - 1) / 2));
         const int j0 = j * TB;
+        if (dist && col_owner(a, j) != a.rank) continue;  // another rank's column
+        // the two shortcuts of the column-to-column hand-over (pre-solve tile parked for the next diagonal tile) need the
+        // neighbouring column on this rank
+        const bool next_local = !dist || (j + 1 < T && col_owner(a, j + 1) == a.rank);
+        const bool prev_local = !dist || (j > 0 && col_owner(a, j - 1) == a.rank);
         const unsigned char *ts = a.ts;
         if (ts && i < T && !ts[(size_t)i * T + j]) continue;  // structurally zero tile: nothing to do, nobody waits for it
         TRACE(t, 0);
@@ -595,20 +706,31 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
             const int c = tid & 63, q = tid >> 6;  // 4 threads per entry, each takes 16 of the 64 k's
             for (int idx = 0; idx < nk; idx++) {
                 const int k = kof(idx);
-                wait_flag(a.flags + (size_t)T * T + k, a.epoch);
-                wait_flag(a.flags + (size_t)j * T + k, a.epoch);
+                wait_flag(a.flags + (size_t)T * T + k, a.epoch, dist);
+                wait_flag(a.flags + (size_t)j * T + k, a.epoch, dist);
                 const double *Lrow = a.H + (size_t)(j0 + c) * ld + k * TB + q * 16;
                 const double *yk = a.b + k * TB + q * 16;
+                for (;;) {
+                    double add = 0.0;
+                    bool bad = false;
 #pragma unroll
-                for (int p = 0; p < 16; p += 2) {
-                    const double2 l = __ldcg(reinterpret_cast<const double2 *>(Lrow + p));
-                    const double2 y = __ldcg(reinterpret_cast<const double2 *>(yk + p));
-                    part = fma(l.x, y.x, fma(l.y, y.y, part));
+                    for (int p = 0; p < 16; p += 2) {
+                        const double2 l = __ldcg(reinterpret_cast<const double2 *>(Lrow + p));
+                        const double2 y = __ldcg(reinterpret_cast<const double2 *>(yk + p));
+                        bad |= is_hole(l.x) | is_hole(l.y) | is_hole(y.x) | is_hole(y.y);
+                        add = fma(l.x, y.x, fma(l.y, y.y, add));
+                    }
+                    if (!dist || !bad) {  // (distributed: the flags are hints, the words validate themselves)
+                        part += add;
+                        break;
+                    }
+                    __nanosleep(100);
                 }
             }
             As[q * TB + c] = part;
-            wait_flag(a.flags + (size_t)j * T + j, a.epoch);
-            load_tile_T(Bs, a.H + (size_t)j0 * ld + j0, ld);  // Bs[k][r] = L_jj[r][k]
+            wait_flag(a.flags + (size_t)j * T + j, a.epoch, dist);
+            if (dist) load_tile_T_valid(Bs, a.H + (size_t)j0 * ld + j0, ld);
+            else load_tile_T(Bs, a.H + (size_t)j0 * ld + j0, ld);  // Bs[k][r] = L_jj[r][k]
             if (tid < TB) dinv[tid] = __ldcg(a.dinv + j0 + tid);
             __syncthreads();
             if (tid < 32) {
@@ -630,10 +752,16 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
                         if (c2 < 32) v0 = yc; else v1 = yc;
                     }
                 }
-                a.b[j0 + tid] = v0;
-                a.b[j0 + 32 + tid] = v1;
+                if (dist) {
+                    mc_store(a.bmc + j0 + tid, v0);
+                    mc_store(a.bmc + j0 + 32 + tid, v1);
+                } else {
+                    a.b[j0 + tid] = v0;
+                    a.b[j0 + 32 + tid] = v1;
+                }
             }
-            publish_flag(a.flags + (size_t)T * T + j, a.epoch);
+            if (dist) publish_flag_mc(a.flags_mc + (size_t)T * T + j, a.epoch);
+            else publish_flag(a.flags + (size_t)T * T + j, a.epoch);
             continue;
         }
 
@@ -674,7 +802,7 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
             // up to 32 steps are polled in one round trip by warp 0, and the tiles of step k+1 are copied asynchronously
             // into the second buffer pair while the tensor cores work on step k.
             // (in list positions: the diagonal tile's step k = j - 1, if it exists, is the fused last one below)
-            const int kend = (i == j && nk > 0 && kof(nk - 1) == j - 1) ? nk - 1 : nk;
+            const int kend = (prev_local && i == j && nk > 0 && kof(nk - 1) == j - 1) ? nk - 1 : nk;
             const int lane = tid & 31, warp = tid >> 5;
             int ready = 0;  // steps at list positions < ready have both of their tiles published
             auto ensure = [&](int k) {
@@ -685,8 +813,8 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
                         const int kp = r + lane;
                         bool ok = kp < kend;
                         const int kk = ok ? kof(kp) : 0;
-                        if (ok) ok = ld_acquire(a.flags + (size_t)i * T + kk) == a.epoch;
-                        if (ok && i != j) ok = ld_acquire(a.flags + (size_t)j * T + kk) == a.epoch;
+                        if (ok) ok = flag_is(a.flags + (size_t)i * T + kk, a.epoch, dist);
+                        if (ok && i != j) ok = flag_is(a.flags + (size_t)j * T + kk, a.epoch, dist);
                         const unsigned m = __ballot_sync(0xffffffffu, ok);
                         r += (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);
                         if (r > k) break;
@@ -717,6 +845,11 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
                     }
                     cp_async_commit();
                     cp_async_wait<1>();
+                    if (dist) {  // the hint flags may have overtaken (part of) the tiles
+                        const int kk = kof(k);
+                        fix_holes((k & 1) ? As2 : As, a.H + (size_t)i0 * ld + kk * TB, ld);
+                        if (i != j) fix_holes((k & 1) ? Bs2 : Bs, a.H + (size_t)j0 * ld + kk * TB, ld);
+                    }
                     __syncthreads();
                     if (k == kend - 1) TRACE(t, 7);
                     const double *Ak = (k & 1) ? As2 : As, *Bk = (k & 1) ? Bs2 : Bs;
@@ -732,7 +865,7 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
         }
         for (int kp = kstart; kp < nk; kp++) {
             const int k = kof(kp);
-            if (MINB == 1 && i == j && k == j - 1) {
+            if (MINB == 1 && prev_local && i == j && k == j - 1) {
                 // Critical path: the diagonal tile's last update needs L_{j,j-1}.  Instead of waiting for the CTA that
                 // owns that tile to solve and publish it (one more trip through L2), take its pre-solve copy -- ready
                 // long before -- and do the tile solve here as soon as L_{j-1,j-1} appears.
@@ -746,11 +879,16 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
                 __syncthreads();
                 continue;
             }
-            wait_flag(a.flags + (size_t)i * T + k, a.epoch);
-            if (i != j) wait_flag(a.flags + (size_t)j * T + k, a.epoch);
+            wait_flag(a.flags + (size_t)i * T + k, a.epoch, dist);
+            if (i != j) wait_flag(a.flags + (size_t)j * T + k, a.epoch, dist);
             TRACE(t, 7);
-            load_tile_R(As, a.H + (size_t)i0 * ld + k * TB, ld);
-            if (i != j) load_tile_R(Bs, a.H + (size_t)j0 * ld + k * TB, ld);
+            if (dist) {
+                load_tile_R_valid(As, a.H + (size_t)i0 * ld + k * TB, ld);
+                if (i != j) load_tile_R_valid(Bs, a.H + (size_t)j0 * ld + k * TB, ld);
+            } else {
+                load_tile_R(As, a.H + (size_t)i0 * ld + k * TB, ld);
+                if (i != j) load_tile_R(Bs, a.H + (size_t)j0 * ld + k * TB, ld);
+            }
             __syncthreads();
             if (i != j) tile_gemm_sub(acc, As, Bs);
             else tile_gemm_sub(acc, As, As, cw, mt0);
@@ -764,16 +902,25 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
             const bool ok = tile_potrf_mma(As, dinv, col, linv8, tmpw, &sh_ok, [&](int t2) { if (t2 < 64) fast_half_store(ft, As, dinv, 0, t2, 64); });  // two warps: more of them slow the pivot chain
             fast_half_store(ft, As, dinv, 1, tid, CT);
             TRACE(t, 4);
-            if (!ok && tid == 0) *a.fail = 1;
+            if (!ok && tid == 0) {
+                *a.fail = a.epoch;
+                if (dist) asm volatile("multimem.st.relaxed.sys.global.b32 [%0], %1;" ::"l"(a.fail_mc), "r"(a.epoch) : "memory");
+            }
             // store L_jj (zero above the diagonal) and 1/diag
             for (int idx = tid; idx < TB * TB / 2; idx += CT) {
                 const int r = idx >> 5, c = (idx & 31) * 2;
                 const double2 v = *reinterpret_cast<const double2 *>(As + r * RS + c);
-                *reinterpret_cast<double2 *>(a.H + (size_t)(i0 + r) * ld + j0 + c) = make_double2(c <= r ? v.x : 0.0, c + 1 <= r ? v.y : 0.0);
+                const double2 w = make_double2(c <= r ? v.x : 0.0, c + 1 <= r ? v.y : 0.0);
+                if (dist) {
+                    mc_store2(a.Hmc + (size_t)(i0 + r) * ld + j0 + c, w.x, w.y);
+                } else {
+                    *reinterpret_cast<double2 *>(a.H + (size_t)(i0 + r) * ld + j0 + c) = w;
+                }
             }
-            if (tid < TB) a.dinv[j0 + tid] = dinv[tid];
+            if (tid < TB) a.dinv[j0 + tid] = dinv[tid];  // (read by this column's own rhs tile only: stays local)
             TRACE(t, 5);
-            publish_flag(a.flags + (size_t)i * T + j, a.epoch);
+            if (dist) publish_flag_mc(a.flags_mc + (size_t)i * T + j, a.epoch);
+            else publish_flag(a.flags + (size_t)i * T + j, a.epoch);
             TRACE(t, 6);
             // Off the critical path (the tile is already published): L_jj^-T = I * L_jj^-T on the tensor cores, so that
             // the backward substitution's per-block triangular solve becomes a 64x64 matrix-vector product.
@@ -784,13 +931,21 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
             }
             __syncthreads();
             tile_trsm_mma(Bs, As, dinv, linv8, tmpw);
-            for (int idx = tid; idx < TB * TB; idx += CT) {
-                const int r = idx >> 6, c = idx & 63;
-                a.linvT[(size_t)j * TB * TB + idx] = Bs[r * RS + c];
+            if (dist) {
+                for (int idx = tid; idx < TB * TB / 2; idx += CT) {
+                    const int r = idx >> 5, c = (idx & 31) * 2;
+                    mc_store2(a.linvT_mc + (size_t)j * TB * TB + r * TB + c, Bs[r * RS + c], Bs[r * RS + c + 1]);
+                }
+                publish_flag_mc(a.lflags_mc + j, a.epoch);
+            } else {
+                for (int idx = tid; idx < TB * TB; idx += CT) {
+                    const int r = idx >> 6, c = idx & 63;
+                    a.linvT[(size_t)j * TB * TB + idx] = Bs[r * RS + c];
+                }
             }
             continue;
         } else {
-            if (MINB == 1 && i == j + 1) {  // park the pre-solve tile in the upper triangle for the next diagonal tile
+            if (MINB == 1 && next_local && i == j + 1) {  // park the pre-solve tile in the upper triangle for the next diagonal tile
                 for (int idx = tid; idx < TB * TB; idx += CT) {
                     const int r = idx >> 6, c = idx & 63;
                     a.H[(size_t)(j0 + r) * ld + i0 + c] = As[r * RS + c];
@@ -800,13 +955,21 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
             TRACE(t, 3);
             tile_trsm_fast(As, Bs, dinv, linv8, tmpw, a.ldiag + (size_t)j * kFastTile);  // L_jj as its halves arrive
             TRACE(t, 4);
-            for (int idx = tid; idx < TB * TB; idx += CT) {
-                const int r = idx >> 6, c = idx & 63;
-                a.H[(size_t)(i0 + r) * ld + j0 + c] = As[r * RS + c];
+            if (dist) {
+                for (int idx = tid; idx < TB * TB / 2; idx += CT) {
+                    const int r = idx >> 5, c = (idx & 31) * 2;
+                    mc_store2(a.Hmc + (size_t)(i0 + r) * ld + j0 + c, As[r * RS + c], As[r * RS + c + 1]);
+                }
+            } else {
+                for (int idx = tid; idx < TB * TB; idx += CT) {
+                    const int r = idx >> 6, c = idx & 63;
+                    a.H[(size_t)(i0 + r) * ld + j0 + c] = As[r * RS + c];
+                }
             }
         }
         TRACE(t, 5);
-        publish_flag(a.flags + (size_t)i * T + j, a.epoch);
+        if (dist) publish_flag_mc(a.flags_mc + (size_t)i * T + j, a.epoch);
+        else publish_flag(a.flags + (size_t)i * T + j, a.epoch);
         TRACE(t, 6);
     }
 }
@@ -821,7 +984,7 @@ __global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
     double *xi = part + 4 * TB;          // [64]
     __shared__ int sh_j;
     const int T = a.T, ld = a.ld, tid = threadIdx.x;
-    const bool failed = *a.fail != 0;
+    const bool dist = a.world > 1;
     for (;;) {
         __syncthreads();
         if (tid == 0) sh_j = T - 1 - atomicAdd(a.counter + 1, 1);
@@ -830,12 +993,18 @@ __global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
         if (j < 0) return;
         const int j0 = j * TB;
         const int c = tid & 63, q = tid >> 6;
+        if (dist) {  // this column's y_j and L_jj^-T come from its owner (the local factor kernel may have finished long before)
+            wait_flag(a.flags + (size_t)T * T + j, a.epoch, true);
+            wait_flag(a.lflags + j, a.epoch, true);
+        }
         {   // Ld <- L_jj^-T (upper triangular); all loads in flight before the first store
             double2 v[TB * TB / 2 / CT];
 #pragma unroll
             for (int u = 0; u < TB * TB / 2 / CT; u++) {
                 const int idx = tid + u * CT;
-                v[u] = __ldcg(reinterpret_cast<const double2 *>(a.linvT + (size_t)j * TB * TB + (idx >> 5) * TB + (idx & 31) * 2));
+                const double2 *src = reinterpret_cast<const double2 *>(a.linvT + (size_t)j * TB * TB + (idx >> 5) * TB + (idx & 31) * 2);
+                v[u] = __ldcg(src);
+                while (dist && (is_hole(v[u].x) | is_hole(v[u].y))) v[u] = __ldcg(src);
             }
 #pragma unroll
             for (int u = 0; u < TB * TB / 2 / CT; u++) {
@@ -845,17 +1014,21 @@ __global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
                 Ld[r * (TB + 1) + k2 + 1] = v[u].y;
             }
         }
-        const double yj = (tid < TB) ? __ldcg(a.b + j0 + tid) : 0.0;  // y_j (from the factor kernel), fetched off the x chain
+        double yj = (tid < TB) ? __ldcg(a.b + j0 + tid) : 0.0;  // y_j (from the factor kernel), fetched off the x chain
+        while (dist && tid < TB && is_hole(yj)) yj = __ldcg(a.b + j0 + tid);
         double s = 0.0;
         for (int i = T - 1; i > j; i--) {
             if (a.ts && !a.ts[(size_t)i * T + j]) continue;  // L_ij is structurally zero
+            if (dist) wait_flag(a.flags + (size_t)i * T + j, a.epoch, true);
             // stage L_ij while x_i may still be in flight
             double2 v[TB * TB / 2 / CT];
 #pragma unroll
             for (int u = 0; u < TB * TB / 2 / CT; u++) {
                 const int idx = tid + u * CT;
                 const int r = idx >> 5, k2 = (idx & 31) * 2;
-                v[u] = __ldcg(reinterpret_cast<const double2 *>(a.H + (size_t)(i * TB + r) * ld + j0 + k2));
+                const double2 *src = reinterpret_cast<const double2 *>(a.H + (size_t)(i * TB + r) * ld + j0 + k2);
+                v[u] = __ldcg(src);
+                while (dist && (is_hole(v[u].x) | is_hole(v[u].y))) v[u] = __ldcg(src);
             }
 #pragma unroll
             for (int u = 0; u < TB * TB / 2 / CT; u++) {
@@ -895,6 +1068,8 @@ __global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
             if (bits == 0ull) bits = 0x8000000000000000ull;
             asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(a.xs + j0 + tid), "l"(bits) : "memory");
             a.b[j0 + tid] = x;
+            // (a failure anywhere was written into every rank's flag before the failing column's tiles were published)
+            const bool failed = *reinterpret_cast<volatile int *>(a.fail) == a.epoch;
             if (j0 + tid < a.n) a.dx[a.rowmap ? a.rowmap[j0 + tid] : j0 + tid] = failed ? 0.0f : (float)x;
         }
     }
@@ -1096,7 +1271,8 @@ cudaError_t launch_small_solve_batch(double *sys, const long long *prob_hoff, co
 
 cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm, float ep, float *dx, int *scratch,
                                 double *dinv, double *linvT, const double *dampdiag, const double *Ain, int epoch,
-                                const unsigned char *tstruct, const int *rowmap, cudaStream_t st, int *launches) {
+                                const unsigned char *tstruct, const int *rowmap, cudaStream_t st, int *launches,
+                                const CholDist *dist) {
     // scratch (ints): [0..1] counters, [2] fail, [16 .. 16+T) unused, [16+T .. 16+2T) preflags, (T+1)*T tile flags, then
     // (16-byte aligned) npad 64-bit words for the backward substitution's x exchange and T * (64*64 + 64) words for the
     // diagonal tiles' fast copies; all zeroed by the memset below
@@ -1108,7 +1284,19 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     }
     // ready flags, counters and the failure flag are reset by one small memset per solve (graph-capturable, and the
     // flags never carry state from one solve to the next)
-    cudaError_t err = cudaMemsetAsync(scratch, 0, chol_scratch_ints(npad) * sizeof(int), st);
+    // (distributed: the tile flags carry the solve's epoch and are never reset -- a reset could wipe what a faster rank has
+    // already published; only the rank-local parts are cleared: counters, the x words, the diagonal tiles' fast copies)
+    const size_t flag_lo = 16, flag_hi = (16 + 2 * (size_t)T + (size_t)(T + 1) * T + 3) & ~(size_t)3;
+    cudaError_t err;
+    if (dist) {
+        if (!Ain || !dist->Hmc || !dist->scratch_mc || !dist->linvT_mc) return cudaErrorInvalidValue;
+        err = cudaMemsetAsync(scratch, 0, 2 * sizeof(int), st);
+        if (err != cudaSuccess) return err;
+        err = cudaMemsetAsync(scratch + flag_hi, 0, (chol_scratch_ints(npad) - flag_hi) * sizeof(int), st);
+    } else {
+        err = cudaMemsetAsync(scratch, 0, chol_scratch_ints(npad) * sizeof(int), st);
+    }
+    (void)flag_lo;
     if (err != cudaSuccess) return err;
     CholArgs a;
     a.H = H;
@@ -1124,7 +1312,19 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     a.flags = scratch + 16 + 2 * T;
     a.xs = reinterpret_cast<unsigned long long *>(scratch + ((16 + 2 * (size_t)T + (size_t)(T + 1) * T + 3) & ~(size_t)3));  // 16-byte aligned
     a.ldiag = a.xs + npad;
-    a.epoch = 1;
+    a.epoch = dist ? dist->epoch : 1;
+    if (dist) {
+        a.rank = dist->rank, a.world = dist->world;
+        a.Hmc = dist->Hmc;
+        a.bmc = dist->Hmc + (size_t)npad * npad;
+        a.linvT_mc = dist->linvT_mc;
+        a.fail_mc = dist->scratch_mc + 2;
+        a.colblk = dist->colblk > 0 ? dist->colblk : 1;
+
+        a.lflags = scratch + 16;
+        a.lflags_mc = dist->scratch_mc + 16;
+        a.flags_mc = dist->scratch_mc + 16 + 2 * T;
+    }
     a.dx = dx;
     a.dinv = dinv;
     a.dampdiag = dampdiag;
@@ -1147,8 +1347,35 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     // large ones are throughput-bound: two CTAs per SM overlap tile loads with the tile GEMMs
     const int ctas = (T >= 400 ? 2 : 1) * sms;
     const int grid = total < ctas ? total : ctas;
+#ifdef VBA_CHOL_TRACE
+    static long long *trace_dev = nullptr;
+    if (dist && std::getenv("VIPE_BA_CHOL_TRACE")) {
+        if (!trace_dev) cudaMalloc(&trace_dev, (size_t)total * 8 * sizeof(long long));
+        cudaMemsetAsync(trace_dev, 0, (size_t)total * 8 * sizeof(long long), st);
+        cudaMemcpyToSymbolAsync(g_trace, &trace_dev, sizeof(trace_dev), 0, cudaMemcpyHostToDevice, st);
+    }
+#endif
     if (T >= 400) chol_factor_kernel<2><<<grid, CT, sm2, st>>>(a);
     else chol_factor_kernel<1><<<grid, CT, sm, st>>>(a);
+#ifdef VBA_CHOL_TRACE
+    if (dist && trace_dev && std::getenv("VIPE_BA_CHOL_TRACE")) {  // developer builds: dump the last solve's stamps
+        cudaStreamSynchronize(st);
+        std::vector<long long> host((size_t)total * 8);
+        cudaMemcpy(host.data(), trace_dev, host.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        char name[256];
+        snprintf(name, sizeof(name), "%s_r%d.txt", std::getenv("VIPE_BA_CHOL_TRACE"), dist->rank);
+        if (FILE *f = fopen(name, "w")) {
+            fprintf(f, "%d %d %d %d\n", T, dist->rank, dist->world, a.colblk);
+            for (int t = 0; t < total; t++) {
+                if (!host[(size_t)t * 8]) continue;
+                fprintf(f, "%d", t);
+                for (int q = 0; q < 8; q++) fprintf(f, " %lld", host[(size_t)t * 8 + q]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
+#endif
     const size_t smb = (size_t)(2 * TB * (TB + 1) + 6 * TB) * sizeof(double);
     err = cudaFuncSetAttribute(chol_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
     if (err != cudaSuccess) return err;

@@ -24,6 +24,11 @@ from . import _lib
 from .ext import slam_ext
 
 
+# from this many unknowns on, collective="auto" distributes the factorisation (C4: 5994; C3's 1794 are latency-bound and
+# stay replicated)
+DIST_SOLVE_MIN_UNKNOWNS = 4096
+
+
 class PeerSystem:
     """Two instances of the reduced camera system [H ; b ; diag(A)] in NVSwitch multicast (symmetric) memory.
 
@@ -52,7 +57,10 @@ class PeerSystem:
 
             _, npad = plan.system_view(plan.workspace(dev))
             count = npad * npad + 2 * npad
-            self.bufs = [symm.empty(count, dtype=torch.float64, device=dev) for _ in range(3)]  # two accumulators + the reduced system
+            self.bufs = [symm.empty(count, dtype=torch.float64, device=dev) for _ in range(3)]  # two accumulators + the reduced system / the factor
+            # auxiliary buffer of the distributed factorisation (ready flags, 1/diag, inverted diagonal tiles): zeroed once, here
+            aux_bytes = int(_lib.lib().vipe_ba_dist_aux_bytes(plan.handle))
+            self.bufs.append(symm.empty((aux_bytes + 7) // 8, dtype=torch.float64, device=dev))
             for b in self.bufs:
                 b.zero_()
             good = True
@@ -110,6 +118,10 @@ class CudaShardEngine:
     def use_solve_buffer(self, local_ptr):
         _lib.check(_lib.lib().vipe_ba_set_solve_buffer(self.plan.handle, local_ptr), "vipe_ba_set_solve_buffer")
 
+    def use_dist_solve(self, factor_local, factor_mc, aux_local, aux_mc, rank, world):
+        _lib.check(_lib.lib().vipe_ba_set_dist_solve(self.plan.handle, factor_local, factor_mc, aux_local, aux_mc, int(rank), int(world)),
+                   "vipe_ba_set_dist_solve")
+
     def use_owned_rows(self, on: bool):
         _lib.check(_lib.lib().vipe_ba_set_owned_rows(self.plan.handle, int(on)), "vipe_ba_set_owned_rows")
 
@@ -129,7 +141,10 @@ def ba_sharded(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, 
     """`slam_ext.ba` sharded by source keyframe across the ranks of `group`.
 
     `collective`: "allreduce" = one NCCL all-reduce of the reduced camera system per iteration; "nvls" = no collective
-    launch at all, the sum is formed by the NVSwitch inside the Cholesky kernel's loads (PeerSystem above); "nvls2" = the
+    launch at all, the sum is formed by the NVSwitch inside the Cholesky kernel's loads (PeerSystem above); "dist" = the same
+    fused input, and the factorisation itself is DISTRIBUTED: tile column j belongs to rank j % world, results are multicast
+    to every rank through the switch (include/vipe_ba.h: vipe_ba_set_dist_solve) -- for large systems, where the replicated
+    solve is what keeps more GPUs from helping; "nvls2" = the
     same in-switch sum as a small kernel of its own (every rank reduces 1/world of the tiles with multimem.ld_reduce and
     multicasts them to all ranks with multimem.st) followed by a solve on local memory; "auto" = "nvls" on 2 GPUs,
     "nvls2" from 4 GPUs on (the fused loads cost the solve 0.14 ms at 8 GPUs), "allreduce" where multicast memory is missing.
@@ -154,16 +169,18 @@ def ba_sharded(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, 
         n_own = int(plan.owned_edges().numel())
         if tuple(targets.shape) != (n_own, 2, ht, wd) or tuple(weights.shape) != (n_own, 2, ht, wd):
             raise RuntimeError(f"owned_inputs: targets/weights must be [{n_own},2,{ht},{wd}] (rows of plan.owned_edges())")
-    peer, two_step = None, False
-    if world > 1 and engine_cls is CudaShardEngine and collective in ("auto", "nvls", "nvls2"):
+    peer, two_step, dist_solve = None, False, False
+    if world > 1 and engine_cls is CudaShardEngine and collective in ("auto", "nvls", "nvls2", "dist"):
         if nvls_available(plan, poses.device, group):
             peer = PeerSystem.get(plan, poses.device, group)
-            two_step = collective == "nvls2" or (collective == "auto" and world >= 4)
-        elif collective in ("nvls", "nvls2"):
+            # the distributed factorisation pays one NVSwitch hop per tile column: worth it once the solve is throughput-bound
+            dist_solve = collective == "dist" or (collective == "auto" and 6 * plan.P >= DIST_SOLVE_MIN_UNKNOWNS)
+            two_step = not dist_solve and (collective == "nvls2" or (collective == "auto" and world >= 4))
+        elif collective in ("nvls", "nvls2", "dist"):
             raise RuntimeError(f"collective='{collective}' needs NVSwitch multicast memory and more than 128 unknowns")
     if profile is not None:
         profile["plan"] = plan
-        profile["collective"] = ("nvls2" if two_step else "nvls") if peer is not None else "allreduce"
+        profile["collective"] = ("dist" if dist_solve else "nvls2" if two_step else "nvls") if peer is not None else "allreduce"
         ev = profile.setdefault("events", [])
     if hasattr(eng, "use_owned_rows"):
         eng.use_owned_rows(bool(owned_inputs))
@@ -173,6 +190,9 @@ def ba_sharded(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, 
         if two_step:  # accumulate in buffer 0, solve in this rank's instance of the reduced system
             eng.use_peer_buffer(peer.bufs[0].data_ptr(), peer.hdls[0].multicast_ptr)
             eng.use_solve_buffer(peer.bufs[2].data_ptr())
+        if dist_solve:
+            eng.use_dist_solve(peer.bufs[2].data_ptr(), peer.hdls[2].multicast_ptr, peer.bufs[3].data_ptr(), peer.hdls[3].multicast_ptr,
+                               rank, world)
         for _ in range(int(iterations)):
             if profile is not None:
                 e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -202,6 +222,8 @@ def ba_sharded(poses, disps, intrinsics, disps_sens, targets, weights, eta, ii, 
             eng.use_peer_buffer(None, None)
             if two_step:
                 eng.use_solve_buffer(None)
+            if dist_solve:
+                eng.use_dist_solve(None, None, None, None, 0, 1)
         if owned_inputs and hasattr(eng, "use_owned_rows"):
             eng.use_owned_rows(False)
     if exchange and world > 1 and not motion_only:

@@ -555,6 +555,9 @@ def main():
                                            "'all_reduce' below is the cross-rank barrier",
                                    "nvls2": "in-switch reduce-scatter + multicast kernel (multimem.ld_reduce / multimem.st) between two "
                                             "cross-rank barriers ('all_reduce' below), then a local solve",
+                                   "dist": "none: the factorisation itself is distributed -- tile columns block-cyclic over the ranks, the owner's "
+                                           "loads sum the partial systems in the switch (multimem.ld_reduce) and L, y, L_jj^-T are multicast to "
+                                           "every rank (multimem.st) as self-validating words; 'all_reduce' below is the cross-rank barrier",
                                    }.get(shard_prof.get("collective"), "NCCL all_reduce of the reduced camera system"),
                     "stage_ms_per_iteration": {"linearize_schur_assemble": shard_stage[0], "all_reduce": shard_stage[1],
                                                "solve_backsub_retract": shard_stage[2]}}
@@ -672,7 +675,7 @@ def main():
                 "edge_pixels_per_sec": value * edge_px,
                 "config": {"workload": workload_name(cfg), "frames": N, "edges": E, "ht": cfg.ht, "wd": cfg.wd,
                            "gn_iterations_per_step": cfg.iters, "lm": cfg.lm, "ep": cfg.ep, "motion_only": cfg.motion_only,
-                           "clips": clips, "parallelism": (f"keyframe-sharded x{world}, " + {"nvls": "in-switch reduction fused into the solve (NVLS)", "nvls2": "in-switch reduce-scatter + multicast (NVLS), local solve"}.get(shard_prof.get("collective"), "NCCL all-reduce per iteration") + ", owner-only targets/weights") if sharded else ("clips batched per rank, no collective" if clips > 1 else "single"),
+                           "clips": clips, "parallelism": (f"keyframe-sharded x{world}, " + {"nvls": "in-switch reduction fused into the solve (NVLS)", "nvls2": "in-switch reduce-scatter + multicast (NVLS), local solve", "dist": "distributed Cholesky over NVSwitch multicast, input summed in the switch"}.get(shard_prof.get("collective"), "NCCL all-reduce per iteration") + ", owner-only targets/weights") if sharded else ("clips batched per rank, no collective" if clips > 1 else "single"),
                            "l2": "flushed between timed steps (256 MB write)", "timing": "cuda events per step, max over ranks",
                            "wall_s_timed_region": wall},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

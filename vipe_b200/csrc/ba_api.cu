@@ -495,12 +495,19 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
         // VIPE_BA_LIN3: "0" = frame-major FMA kernels only; "1" (default) = the TMA-fed pipeline for motion-only runs
         const char *env = std::getenv("VIPE_BA_LIN3");
         const int mode = env ? std::atoi(env) : 1;
-        p->use_lin3 = mode >= 1 && p->packed && lin3_supported(p->HW, p->NT * p->PPT);
+        p->use_lin3 = mode >= 1 && p->packed;  // (the motion-only tile shape is fixed further down; checked there)
     }
     // motion-only shares the partial layout (ntile), so it uses the same tile shape
     p->NTm = p->NT;
     p->PPTm = p->PPT;
     p->ntile_m = p->ntile;
+    if (p->use_lin4 && p->HW % 512 == 0) {
+        // motion-only runs keep their own, wide tile (they have no staging buffer): the partial layout is chosen per call
+        p->NTm = 256;
+        p->PPTm = 2;
+        p->ntile_m = p->HW / 512;
+    }
+    p->use_lin3 = p->use_lin3 && lin3_supported(p->HW, p->NTm * p->PPTm);
 
     // partial-buffer offsets
     p->gbase.assign(K + 1, 0);
@@ -600,7 +607,7 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     p->off_econst2 = take(sizeof(float) * 32 * (p->use_lin4 ? (size_t)std::max<int64_t>(E, 1) : 1));
     p->off_sq = take(sizeof(float) * (p->use_lin4 ? (size_t)K * p->HW : 1));
     p->off_sqw = take(sizeof(float) * (p->use_lin4 ? (size_t)K * p->HW : 1));
-    p->off_epart = take(sizeof(float) * (size_t)std::max<int64_t>(E, 1) * (p->use_lin4 ? std::max(p->ntile, p->HW / 64) : p->ntile) * kEdgeStride);
+    p->off_epart = take(sizeof(float) * (size_t)std::max<int64_t>(E, 1) * std::max(p->use_lin4 ? std::max(p->ntile, p->HW / 64) : p->ntile, p->ntile_m) * kEdgeStride);
     p->off_gpart = take(sizeof(float) * (size_t)std::max<long long>(p->gbase[K], 1));
     p->off_msc = take(sizeof(double) * (size_t)std::max<long long>(p->mbase[K], 1));
     p->off_q = take(sizeof(float) * (size_t)K * p->HW);
@@ -814,6 +821,7 @@ static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void 
     la.gpart = (float *)(w + p->off_gpart);
     la.qbuf = (float *)(w + p->off_q);
     la.qwbuf = (float *)(w + p->off_qw);
+    if (motion_only) la.tb.ntile = la.tb.ntile_e = p->ntile_m;  // the motion-only kernels tile a frame their own way
     if (p->use_lin4 && !motion_only) {
         la.tb.ntile_e = p->HW / 64;  // one edge record per 64-pixel unit
         Lin4Launch l4;
@@ -834,12 +842,12 @@ static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void 
         p->launches += 3;
     } else if (p->packed && motion_only && p->use_lin3) {
         const int slot_lo = p->fptr[p->k_lo], nslots = p->fptr[p->k_hi] - slot_lo;
-        VBA_CUDA(launch_lin3_motion(la, (const int *)(w + p->off_slot_src), slot_lo, nslots, p->NT * p->PPT, (float *)(w + p->off_econst),
+        VBA_CUDA(launch_lin3_motion(la, (const int *)(w + p->off_slot_src), slot_lo, nslots, p->NTm * p->PPTm, (float *)(w + p->off_econst),
                                     device_sm_count(), st));
         p->launches += 2;
     } else {
         if (p->packed)
-            VBA_CUDA(launch_linearize2(la, nframes, std::max(p->dmax, 1), motion_only != 0, p->NT, st));
+            VBA_CUDA(launch_linearize2(la, nframes, std::max(p->dmax, 1), motion_only != 0, motion_only ? p->NTm : p->NT, st));
         else
             VBA_CUDA(launch_linearize(la, nframes, std::max(p->dmax, 1), motion_only != 0, p->NT, p->PPT, st));
         p->launches++;

@@ -636,7 +636,8 @@ __device__ __forceinline__ void acc_to_smem_rs(const double (&acc)[8][2], double
 __device__ __forceinline__ void acc_to_smem_rs(const double (&acc)[8][2], double *S) { acc_to_smem_rs(acc, S, threadIdx.x >> 5); }
 
 // MINB = 1: latency-bound sizes, the whole register file for the unrolled register kernels; MINB = 2: throughput-bound
-template <int MINB>
+// DIST: the distributed factorisation (a compile-time switch: the single-GPU kernel is latency-bound and keeps its exact code)
+template <int MINB, bool DIST>
 __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a) {
     extern __shared__ __align__(16) double sm[];
     double *As = sm;             // [64][RS]
@@ -651,7 +652,7 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
     __shared__ unsigned short klist[kMaxSparseT];
     const int T = a.T, ld = a.ld, tid = threadIdx.x;
     const int total = T * (T + 1) / 2 + T;  // lower tiles + one rhs tile per column
-    const bool dist = a.world > 1;
+    constexpr bool dist = DIST;
     for (;;) {
         __syncthreads();
         if (tid == 0) {
@@ -976,6 +977,7 @@ __global__ void __launch_bounds__(CT, MINB) chol_factor_kernel(const CholArgs a)
 
 // backward substitution x = L^-T y, one CTA per column block (claimed in descending order).
 // The diagonal tile and 1/diag are staged before the first wait so that only the x_i chain is exposed.
+template <bool DIST>
 __global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
     extern __shared__ __align__(16) double bsm[];
     double *Ld = bsm;                    // [64][65] L_jj
@@ -984,7 +986,8 @@ __global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
     double *xi = part + 4 * TB;          // [64]
     __shared__ int sh_j;
     const int T = a.T, ld = a.ld, tid = threadIdx.x;
-    const bool dist = a.world > 1;
+    constexpr bool dist = DIST;
+    const bool failed0 = !DIST && *a.fail == a.epoch;  // (one GPU: the factorisation is complete when this kernel starts)
     for (;;) {
         __syncthreads();
         if (tid == 0) sh_j = T - 1 - atomicAdd(a.counter + 1, 1);
@@ -1069,7 +1072,7 @@ __global__ void __launch_bounds__(CT) chol_backward_kernel(const CholArgs a) {
             asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(a.xs + j0 + tid), "l"(bits) : "memory");
             a.b[j0 + tid] = x;
             // (a failure anywhere was written into every rank's flag before the failing column's tiles were published)
-            const bool failed = *reinterpret_cast<volatile int *>(a.fail) == a.epoch;
+            const bool failed = DIST ? *reinterpret_cast<volatile int *>(a.fail) == a.epoch : failed0;
             if (j0 + tid < a.n) a.dx[a.rowmap ? a.rowmap[j0 + tid] : j0 + tid] = failed ? 0.0f : (float)x;
         }
     }
@@ -1335,9 +1338,13 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     // MINB = 1 double-buffers the tiles of its k-loop (4 tile buffers); MINB = 2 keeps two so that two CTAs fit an SM
     const size_t sm = (size_t)(4 * TB * RS + 2 * TB + 8 * 96 + 8 * 160) * sizeof(double);
     const size_t sm2 = (size_t)(2 * TB * RS + 2 * TB + 8 * 96 + 8 * 160) * sizeof(double);
-    err = cudaFuncSetAttribute(chol_factor_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    err = cudaFuncSetAttribute(chol_factor_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (err != cudaSuccess) return err;
-    err = cudaFuncSetAttribute(chol_factor_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+    err = cudaFuncSetAttribute(chol_factor_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+    if (err != cudaSuccess) return err;
+    err = cudaFuncSetAttribute(chol_factor_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (err != cudaSuccess) return err;
+    err = cudaFuncSetAttribute(chol_factor_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
     if (err != cudaSuccess) return err;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -1345,7 +1352,9 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     const int total = T * (T + 1) / 2 + T;
     // small systems are latency-bound: one CTA per SM gives the critical-path tiles a whole fp64 pipe;
     // large ones are throughput-bound: two CTAs per SM overlap tile loads with the tile GEMMs
-    const int ctas = (T >= 400 ? 2 : 1) * sms;
+    // (measured at C4, T = 94: two CTAs per SM instead of one change the solve by 2 %, 3.62 vs 3.70 ms)
+    constexpr int t2 = 400;  // tile count from which two CTAs share an SM
+    const int ctas = (T >= t2 ? 2 : 1) * sms;
     const int grid = total < ctas ? total : ctas;
 #ifdef VBA_CHOL_TRACE
     static long long *trace_dev = nullptr;
@@ -1355,8 +1364,13 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
         cudaMemcpyToSymbolAsync(g_trace, &trace_dev, sizeof(trace_dev), 0, cudaMemcpyHostToDevice, st);
     }
 #endif
-    if (T >= 400) chol_factor_kernel<2><<<grid, CT, sm2, st>>>(a);
-    else chol_factor_kernel<1><<<grid, CT, sm, st>>>(a);
+    if (dist) {
+        if (T >= t2) chol_factor_kernel<2, true><<<grid, CT, sm2, st>>>(a);
+        else chol_factor_kernel<1, true><<<grid, CT, sm, st>>>(a);
+    } else {
+        if (T >= t2) chol_factor_kernel<2, false><<<grid, CT, sm2, st>>>(a);
+        else chol_factor_kernel<1, false><<<grid, CT, sm, st>>>(a);
+    }
 #ifdef VBA_CHOL_TRACE
     if (dist && trace_dev && std::getenv("VIPE_BA_CHOL_TRACE")) {  // developer builds: dump the last solve's stamps
         cudaStreamSynchronize(st);
@@ -1377,9 +1391,12 @@ cudaError_t launch_damped_solve(double *H, double *b, int n, int npad, float lm,
     }
 #endif
     const size_t smb = (size_t)(2 * TB * (TB + 1) + 6 * TB) * sizeof(double);
-    err = cudaFuncSetAttribute(chol_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+    err = cudaFuncSetAttribute(chol_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
     if (err != cudaSuccess) return err;
-    chol_backward_kernel<<<T < sms ? T : sms, CT, smb, st>>>(a);
+    err = cudaFuncSetAttribute(chol_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+    if (err != cudaSuccess) return err;
+    if (dist) chol_backward_kernel<true><<<T < sms ? T : sms, CT, smb, st>>>(a);
+    else chol_backward_kernel<false><<<T < sms ? T : sms, CT, smb, st>>>(a);
     if (launches) *launches += 2;
     return cudaGetLastError();
 }

@@ -52,6 +52,10 @@ struct vipe_ba_plan {
     bool packed = false;  // linearize2 (pixel-pair) kernel
     int NTm = 256, PPTm = 1, ntile_m = 0;  // motion-only tile shape (no staging buffer => always the widest)
     int k_lo = 0, k_hi = 0, dmax = 0;
+    // source frames whose staging buffer does not fit shared memory go through global memory in a launch of their own
+    std::vector<int> flist_hub, flist_bulk;
+    int dmax_bulk = 0;
+    size_t off_flist_hub = 0, off_flist_bulk = 0, off_uglobal = 0, off_fscratch = 0;
     bool use_lin3 = false;  // TMA-fed motion-only pipeline (ba_lin3.cu)
     size_t off_econst = 0, off_slot_src = 0;
     std::vector<int> slot_src;
@@ -467,12 +471,34 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     compute_elimination_order(p);
     build_assembly_lists(p);
 
-    if (tile_config2(p->HW, std::max(p->dmax, 1), false, p->NT)) {
+    // Tile shape from the out-degrees.  Up to kHubDegree edges per source frame it follows the largest degree, as it always
+    // did.  Beyond that the tile follows kHubDegree and the frames whose staging buffer would not fit shared memory ("hub"
+    // frames; the reference has no out-degree limit) run in a second launch that stages in global memory -- a single hub no
+    // longer forces the narrowest tile on every frame, and no degree makes plan creation fail on the packed path.
+    constexpr int kHubDegree = 32;
+    if (tile_config2(p->HW, std::max(std::min(p->dmax, kHubDegree), 1), false, p->NT)) {
         p->packed = true;
         p->PPT = 2;
+        if (p->dmax > kHubDegree) {
+            for (int k = p->k_lo; k < p->k_hi; k++) {
+                const int d = p->fptr[k + 1] - p->fptr[k];
+                if (lin2_staging_bytes(d, p->NT) > lin2_staging_cap()) {
+                    p->flist_hub.push_back(k);
+                } else {
+                    p->flist_bulk.push_back(k);
+                    p->dmax_bulk = std::max(p->dmax_bulk, d);
+                }
+            }
+            if (p->flist_hub.empty()) {
+                p->flist_bulk.clear();  // everything fits: one launch
+            } else if (p->NT > 64) {
+                delete p;
+                return fail("internal: hub frames need the 64- or 32-slot tile");
+            }
+        }
     } else if (!tile_config(p->HW, std::max(p->dmax, 1), false, p->NT, p->PPT)) {
         delete p;
-        return fail("a source frame has too many outgoing edges for the shared-memory staging buffer");
+        return fail("a source frame has too many outgoing edges for the shared-memory staging buffer (odd ht*wd: scalar kernels)");
     }
     {
         // VIPE_BA_LIN4: "1" = the two-kernel Blackwell pipeline of ba_lin4.cu (disparity blocks first, then asynchronously
@@ -581,6 +607,8 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     p->off_lin4_units = take(sizeof(Lin4Unit) * std::max<size_t>(p->lin4_units.size(), 1));
     p->off_lin4_cta_item = take(sizeof(int) * std::max<size_t>(p->lin4_cta_item.size(), 1));
     p->off_lin4_cta_unit = take(sizeof(int) * std::max<size_t>(p->lin4_cta_unit.size(), 1));
+    p->off_flist_hub = take(sizeof(int) * std::max<size_t>(p->flist_hub.size(), 1));
+    p->off_flist_bulk = take(sizeof(int) * std::max<size_t>(p->flist_bulk.size(), 1));
     p->slot_src.assign(std::max<int64_t>(E, 1), 0);
     for (int k = 0; k < K; k++)
         for (int s2 = p->fptr[k]; s2 < p->fptr[k + 1]; s2++) p->slot_src[s2] = p->kx32[k];
@@ -608,6 +636,12 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     p->off_sq = take(sizeof(float) * (p->use_lin4 ? (size_t)K * p->HW : 1));
     p->off_sqw = take(sizeof(float) * (p->use_lin4 ? (size_t)K * p->HW : 1));
     p->off_epart = take(sizeof(float) * (size_t)std::max<int64_t>(E, 1) * std::max(p->use_lin4 ? std::max(p->ntile, p->HW / 64) : p->ntile, p->ntile_m) * kEdgeStride);
+    {
+        const size_t own_slots = (size_t)(p->fptr[p->k_hi] - p->fptr[p->k_lo]);
+        p->off_uglobal = take(sizeof(float) * (p->flist_hub.empty() ? 1 : own_slots * p->ntile * 6 * (size_t)(p->NT * p->PPT)));
+        // frame_reduce keeps 126 doubles per edge; beyond ~240 edges per frame that no longer fits shared memory
+        p->off_fscratch = take(sizeof(double) * (p->dmax > 200 ? own_slots * kReduceDoubles : 1));
+    }
     p->off_gpart = take(sizeof(float) * (size_t)std::max<long long>(p->gbase[K], 1));
     p->off_msc = take(sizeof(double) * (size_t)std::max<long long>(p->mbase[K], 1));
     p->off_q = take(sizeof(float) * (size_t)K * p->HW);
@@ -656,6 +690,8 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     std::memcpy(p->blob.data() + p->off_rowmap, p->rowmap.data(), sizeof(int) * p->npad);
     if (!p->tstruct.empty()) std::memcpy(p->blob.data() + p->off_tstruct, p->tstruct.data(), p->tstruct.size());
     std::memcpy(p->blob.data() + p->off_slot_src, p->slot_src.data(), sizeof(int) * p->slot_src.size());
+    put(p->off_flist_hub, p->flist_hub.data(), sizeof(int) * p->flist_hub.size());
+    put(p->off_flist_bulk, p->flist_bulk.data(), sizeof(int) * p->flist_bulk.size());
     put(p->off_lin4_items, p->lin4_items.data(), sizeof(Lin4Item) * p->lin4_items.size());
     put(p->off_lin4_units, p->lin4_units.data(), sizeof(Lin4Unit) * p->lin4_units.size());
     put(p->off_lin4_cta_item, p->lin4_cta_item.data(), sizeof(int) * p->lin4_cta_item.size());
@@ -846,7 +882,15 @@ static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void 
                                     device_sm_count(), st));
         p->launches += 2;
     } else {
-        if (p->packed)
+        if (p->packed && !motion_only && !p->flist_hub.empty()) {
+            la.uglobal = (float *)(w + p->off_uglobal);
+            la.flist = (const int *)(w + p->off_flist_hub);  // the long CTAs first
+            VBA_CUDA(launch_linearize2(la, (int)p->flist_hub.size(), std::max(p->dmax, 1), false, p->NT, st, true));
+            la.flist = (const int *)(w + p->off_flist_bulk);
+            VBA_CUDA(launch_linearize2(la, (int)p->flist_bulk.size(), std::max(p->dmax_bulk, 1), false, p->NT, st));
+            la.flist = nullptr;
+            p->launches++;
+        } else if (p->packed)
             VBA_CUDA(launch_linearize2(la, nframes, std::max(p->dmax, 1), motion_only != 0, motion_only ? p->NTm : p->NT, st));
         else
             VBA_CUDA(launch_linearize(la, nframes, std::max(p->dmax, 1), motion_only != 0, p->NT, p->PPT, st));
@@ -888,6 +932,7 @@ static int linearize_impl(const vipe_ba_plan *p, const vipe_ba_tensors *t, void 
     ra.msc = (double *)(w + p->off_msc);
     ra.hsys = H;
     ra.motion_only = motion_only;
+    ra.fscratch = p->dmax > 200 ? (double *)(w + p->off_fscratch) : nullptr;
     ra.cblk = (double *)(w + p->off_cblk);
     ra.cvec = (double *)(w + p->off_cvec);
     ra.cvec2 = (double *)(w + p->off_cvec2);

@@ -89,6 +89,9 @@ struct LinArgs {
     float *qbuf;   // [K][HW]  Q = 1/C
     float *qwbuf;  // [K][HW]  Q*w
     const int *flist = nullptr;  // DEV: kx positions of the frames this launch covers (null: k_lo + blockIdx.y)
+    // staging of the pose-disparity vectors u in GLOBAL memory, for source frames with more outgoing edges than the
+    // shared-memory staging buffer holds: [owned edge slots][ntile][6][TILE] floats
+    float *uglobal = nullptr;
 };
 
 constexpr int kFocalNT = 256;     // the focal pass tiles a frame into 256-pixel tiles of its own
@@ -106,6 +109,8 @@ struct FocalArgs {
     int ntile_f, motion_only;
 };
 
+constexpr int kReduceDoubles = 36 + 36 + 27 + 6 + 14 + 6 + 1;  // G, T, summed records, g, focal records, border column, target index
+
 struct ReduceArgs {
     Tables tb;
     const float *poses;
@@ -115,6 +120,9 @@ struct ReduceArgs {
     float focal_lm = 0.0f;
     double *msc;   // M scratch (used when a frame's blocks do not fit shared memory)
     int msc_smem = 0;  // 1: M lives in the kernel's shared memory (set by launch_frame_reduce)
+    double *fscratch = nullptr;  // per-edge working set [E_owned][kReduceDoubles] in global memory, used when a frame's does not
+                                 // fit shared memory (hub frames; set by launch_frame_reduce when needed)
+    int fs_global = 0;
     // Deterministic assembly: every frame writes its 6x6 block / 6-vector contributions to fixed slots of `cblk` / `cvec`
     // (`cvec2`: the same slots for diag(A)); assemble_kernel then sums the slots of each destination in a fixed order.
     double *cblk = nullptr;           // [sum over owned frames of (npairs + d + 1)][36]

@@ -366,7 +366,9 @@ __global__ void __launch_bounds__(256) frame_reduce_kernel(const ReduceArgs a) {
     const int ai = tb.pose_sys[src];
     const size_t cb = (size_t)a.cbase[k], vb = (size_t)a.vbase[k];
 
-    double *G = dsm;            // [d][36]
+    // hub frames: the per-edge working set lives in global memory (same code, the CTA's barriers order its accesses)
+    double *const wbase = a.fs_global ? a.fscratch + (size_t)(s0 - tb.slot_lo) * kReduceDoubles : dsm;
+    double *G = wbase;          // [d][36]
     double *T = G + d * 36;     // [d][36]
     double *hs = T + d * 36;    // [d][27]   summed edge records
     double *gv = hs + d * 27;   // [d][6]    g_m
@@ -907,6 +909,11 @@ cudaError_t launch_frame_reduce(const ReduceArgs &a, int nframes, int dmax, cuda
     ReduceArgs b = a;
     b.msc_smem = (sm + msc_bytes <= 96 * 1024) ? 1 : 0;  // backend degrees (~10-20 edges per frame) fit; hubs fall back to global
     if (b.msc_smem) sm += msc_bytes;
+    if (sm > 200 * 1024) {  // hub frames beyond shared memory: everything per edge moves to the global scratch
+        if (!a.fscratch) return cudaErrorInvalidValue;
+        b.fs_global = 1;
+        sm = 64;
+    }
     cudaError_t err = cudaFuncSetAttribute(frame_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (err != cudaSuccess) return err;
     frame_reduce_kernel<<<nframes, 256, sm, st>>>(b);

@@ -13,7 +13,10 @@ bool tile_config(int HW, int dmax, bool motion, int &NT, int &PPT);
 cudaError_t launch_linearize(const LinArgs &a, int nframes, int dmax, bool motion, int NT, int PPT, cudaStream_t st);
 // packed 2-pixels-per-thread variant (ba_linearize2.cu); needs an even HW.  TILE = 2 * NT.
 bool tile_config2(int HW, int dmax, bool motion, int &NT);
-cudaError_t launch_linearize2(const LinArgs &a, int nframes, int dmax, bool motion, int NT, cudaStream_t st);
+cudaError_t launch_linearize2(const LinArgs &a, int nframes, int dmax, bool motion, int NT, cudaStream_t st, bool ug = false);
+// shared-memory bytes of the packed kernel's staging buffer for out-degree d, and what a CTA may use
+size_t lin2_staging_bytes(int d, int NT);
+size_t lin2_staging_cap();
 // TMA-fed motion-only pipeline (ba_lin3.cu); `econst_dev` is E x 16 floats of scratch for the per-edge constants.
 bool lin3_supported(int HW, int chunk_px);
 // motion-only variant: flat (edge slot, chunk) units over the slots [slot_lo, slot_lo + nslots); `slot_src_dev[slot]` = source frame id

@@ -47,7 +47,15 @@ __device__ __forceinline__ float group8_transpose_reduce(float (&v)[8], int lane
 // NT = pixel-pair slots per tile (TILE = 2 NT pixels); the CTA has 2 NT threads: the two halves share the tile's
 // pixels and split its edges (even / odd), which doubles the warps per SM at the same shared-memory footprint
 // (the staging buffer, not registers, bounds occupancy).
-template <int NT, bool MOTION>
+// UG: the staging buffer U lives in global memory (a.uglobal) instead of shared memory -- for source frames with more
+// outgoing edges than shared memory holds (the reference has no out-degree limit); same code, L2 instead of shared memory.
+template <bool UG>
+__device__ __forceinline__ float4 ldu4(const float *p) {
+    if (UG) return __ldcg(reinterpret_cast<const float4 *>(p));
+    return *reinterpret_cast<const float4 *>(p);
+}
+
+template <int NT, bool MOTION, bool UG = false>
 __global__ void __launch_bounds__(2 * NT, (MOTION && NT == 256) ? 2 : 1) linearize2_kernel(const LinArgs a) {
     constexpr int TILE = NT * 2;
     constexpr int NW = NT / 32;   // warps per half
@@ -66,8 +74,9 @@ __global__ void __launch_bounds__(2 * NT, (MOTION && NT == 256) ? 2 : 1) lineari
 
     float2 *ec2 = reinterpret_cast<float2 *>(smem);           // [d][kEc2] duplicated edge constants
     float *red = smem + 2 * kEc2 * d;                         // [d][NW][27]
-    float *U = red + ((d * NW * kEdgeVals + 3) & ~3);         // [6d][TILE]
-    float *Qs = U + (MOTION ? 0 : 6 * d * TILE);              // [TILE]
+    float *const after_red = red + ((d * NW * kEdgeVals + 3) & ~3);
+    float *U = UG ? a.uglobal + ((size_t)(s0 - tb.slot_lo) * tb.ntile + (size_t)tile * d) * 6 * TILE : after_red;  // [6d][TILE]
+    float *Qs = (UG || MOTION) ? after_red : U + 6 * d * TILE;  // [TILE]
     float *Ws = Qs + TILE;                                    // [TILE]
 
     for (int m = tid; m < d; m += NTH) {
@@ -278,7 +287,7 @@ __global__ void __launch_bounds__(2 * NT, (MOTION && NT == 256) ? 2 : 1) lineari
                 const float4 q4 = *reinterpret_cast<const float4 *>(Qs + px);
                 float4 ua4[6];
 #pragma unroll
-                for (int r = 0; r < 6; r++) ua4[r] = *reinterpret_cast<const float4 *>(Um + r * TILE + px);
+                for (int r = 0; r < 6; r++) ua4[r] = ldu4<UG>(Um + r * TILE + px);
                 float2 ualo[6], uahi[6];
 #pragma unroll
                 for (int r = 0; r < 6; r++) {
@@ -286,11 +295,11 @@ __global__ void __launch_bounds__(2 * NT, (MOTION && NT == 256) ? 2 : 1) lineari
                     uahi[r] = fmul2(make_float2(ua4[r].z, ua4[r].w), make_float2(q4.z, q4.w));
                 }
                 // the next column block is loaded while the current one is consumed (one LDS latency per step instead of six)
-                float4 ubn = *reinterpret_cast<const float4 *>(Up + px);
+                float4 ubn = ldu4<UG>(Up + px);
 #pragma unroll
                 for (int c2 = 0; c2 < 6; c2++) {
                     const float4 ub4 = ubn;
-                    if (c2 < 5) ubn = *reinterpret_cast<const float4 *>(Up + (c2 + 1) * TILE + px);
+                    if (c2 < 5) ubn = ldu4<UG>(Up + (c2 + 1) * TILE + px);
                     else if (diag) ubn = *reinterpret_cast<const float4 *>(Ws + px);
                     const float2 blo = make_float2(ub4.x, ub4.y), bhi = make_float2(ub4.z, ub4.w);
 #pragma unroll
@@ -332,12 +341,14 @@ __global__ void __launch_bounds__(2 * NT, (MOTION && NT == 256) ? 2 : 1) lineari
 }
 
 // =================================================================================================
-static size_t lin2_smem_bytes(int d, int NT, bool motion) {
+static size_t lin2_smem_bytes(int d, int NT, bool motion, bool ug = false) {
     const int NW = NT / 32, TILE = NT * 2;
     size_t fl = (size_t)2 * kEc2 * d + (((size_t)d * NW * kEdgeVals + 3) & ~(size_t)3);
-    fl += motion ? 2 * TILE : (size_t)6 * d * TILE + 2 * TILE;
+    fl += (motion || ug) ? 2 * TILE : (size_t)6 * d * TILE + 2 * TILE;
     return fl * sizeof(float);
 }
+size_t lin2_staging_bytes(int d, int NT) { return lin2_smem_bytes(d, NT, false); }
+size_t lin2_staging_cap() { return 200 * 1024; }
 
 bool tile_config2(int HW, int dmax, bool motion, int &NT) {
     if (HW % 2 != 0) return false;
@@ -362,10 +373,11 @@ bool tile_config2(int HW, int dmax, bool motion, int &NT) {
     return false;
 }
 
-template <int NT, bool MOTION>
+template <int NT, bool MOTION, bool UG = false>
 static cudaError_t launch_lin2_t(const LinArgs &a, int nframes, int dmax, cudaStream_t st) {
-    const size_t sm = lin2_smem_bytes(dmax, NT, MOTION);
-    auto kern = linearize2_kernel<NT, MOTION>;
+    const size_t sm = lin2_smem_bytes(dmax, NT, MOTION, UG);
+    if (sm > 227 * 1024) return cudaErrorInvalidValue;
+    auto kern = linearize2_kernel<NT, MOTION, UG>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (err != cudaSuccess) return err;
     dim3 grid(a.tb.ntile, nframes);
@@ -373,8 +385,14 @@ static cudaError_t launch_lin2_t(const LinArgs &a, int nframes, int dmax, cudaSt
     return cudaGetLastError();
 }
 
-cudaError_t launch_linearize2(const LinArgs &a, int nframes, int dmax, bool motion, int NT, cudaStream_t st) {
+cudaError_t launch_linearize2(const LinArgs &a, int nframes, int dmax, bool motion, int NT, cudaStream_t st, bool ug) {
     if (nframes <= 0) return cudaSuccess;
+    if (ug) {  // hub frames: u staged in global memory (the narrow tiles are the ones a plan with hub frames uses)
+        if (motion || !a.uglobal) return cudaErrorInvalidValue;
+        if (NT == 64) return launch_lin2_t<64, false, true>(a, nframes, dmax, st);
+        if (NT == 32) return launch_lin2_t<32, false, true>(a, nframes, dmax, st);
+        return cudaErrorInvalidValue;
+    }
 #define VBA_LIN2(NT_)                                                                                    \
     if (NT == NT_)                                                                                       \
         return motion ? launch_lin2_t<NT_, true>(a, nframes, dmax, st) : launch_lin2_t<NT_, false>(a, nframes, dmax, st);

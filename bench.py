@@ -537,6 +537,7 @@ def main():
     deg = torch.bincount(pr.ii, minlength=N).double()
     gram_ops = float((36.0 * deg * (deg + 1) / 2 + 12.0 * deg).sum()) * HW
     lin_fma_ops = (110.0 * E * HW + (0.0 if cfg.motion_only else gram_ops)) * nprob
+    FP64_DMMA_PEAK_TFLOPS = 37.2  # measured (scripts/dmma_lat.cu): 64 DMMA FMA/clk/SM x 148 SMs x 1.965 GHz x 2
     FP32_PEAK_TFMA = 34.3  # measured on this pool: FFMA/FFMA2 full-chip micro-benchmark (scripts/ffma2_micro.cu), TFMA/s
     roofline = None
     if sharded:
@@ -575,6 +576,16 @@ def main():
                                 "note": "the fused Jacobian+Schur kernel is FMA-bound at backend degrees; see DESIGN.md section 4"},
                     "whole_iteration": {"algorithmic_bytes": it_bytes,
                                         "achieved_gbs": it_bytes * cfg.iters * (clips // nprob if batched else clips) * args.steps / (total_ms * 1e-3) / 1e9 / max(world, 1)}}
+        if not cfg.motion_only and clips == 1:
+            # the largest share of the iteration: the fp64 Cholesky of the reduced camera system (solve stage = memset + factor +
+            # backward substitution), against the fp64 tensor (DMMA) rate measured on B200
+            n_sys = 6 * (pr.t1 - pr.t0)
+            solve_ms = stage_ms[2] / stage_iters
+            roofline["solver"] = {"kernel": "vba::chol_factor_kernel + chol_backward_kernel (tile-dataflow fp64 Cholesky, DMMA)", "bound": "tensor (fp64)",
+                                  "unknowns": n_sys, "flop": n_sys ** 3 / 3.0, "avg_stage_ms": solve_ms,
+                                  "achieved": n_sys ** 3 / 3.0 / (solve_ms * 1e-3) / 1e12, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                                  "frac": n_sys ** 3 / 3.0 / (solve_ms * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
+                                  "note": "C3: bound by the latency of the chain of tile columns, not by the pipe; C4: throughput-bound"}
         if jac_ms:
             _, jac_bytes = algorithmic_bytes(cfg, E, K, N, HW, True)
             roofline["jacobian_stage_alone"] = {

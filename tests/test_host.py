@@ -162,3 +162,26 @@ def test_identity_plan_cache_keeps_several_graphs(lib_built):
     # a shard's plan is its own entry
     assert slam_ext.ba_plan(ii, jj, 9, 8, 8, 1, 9, 1, 2) is not p2
     assert slam_ext.ba_plan(ii, jj, 9, 8, 8, 1, 9, 1, 2) is slam_ext.ba_plan(ii, jj, 9, 8, 8, 1, 9, 1, 2)
+
+
+@pytest.mark.parametrize("deg", [40, 150, 300, 650])
+def test_plan_accepts_hub_frames(lib_built, deg):
+    """A source frame with far more outgoing edges than the shared-memory staging buffer holds (the reference has no out-degree
+    limit) must not make plan creation fail: hub frames get a launch of their own that stages through global memory."""
+    from vipe_b200.plan import BAPlan
+
+    n = deg + 1
+    others = torch.arange(1, n)
+    ii = torch.cat([torch.zeros(deg, dtype=torch.int64), others])
+    jj = torch.cat([others, torch.zeros(deg, dtype=torch.int64)])
+    plan = BAPlan(ii, jj, n, 8, 16, 1, n)
+    assert plan.P == n - 1
+    bk = O.bookkeeping(ii, jj, 1, n)
+    assert torch.equal(plan.kx, bk.kx)
+    assert int(_max_degree(plan)) == deg
+
+
+def _max_degree(plan):
+    from vipe_b200 import _lib
+
+    return _lib.lib().vipe_ba_plan_max_degree(plan.handle)

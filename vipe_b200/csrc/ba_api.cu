@@ -476,10 +476,27 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
     // frames; the reference has no out-degree limit) run in a second launch that stages in global memory -- a single hub no
     // longer forces the narrowest tile on every frame, and no degree makes plan creation fail on the packed path.
     constexpr int kHubDegree = 32;
-    if (tile_config2(p->HW, std::max(std::min(p->dmax, kHubDegree), 1), false, p->NT)) {
+    int tile_degree = std::min(p->dmax, kHubDegree);  // the degree the tile shape is chosen for
+    if (p->HW % 2 == 0 && p->dmax > 1) {
+        // The widest tile (512 pixels: one partial record per 512 pixels, the least traffic for frame_reduce) holds up to d512
+        // edges.  If all but a few frames fit it, they get it and the few run as hub frames (C4: 996 of 1000 frames have <= 16
+        // edges, the largest 18 -- which would put every frame on 128-pixel tiles, 4x the Gram partials).
+        int d512 = 0;
+        while (lin2_staging_bytes(d512 + 1, 256) <= lin2_staging_cap()) d512++;
+        if (p->dmax > d512 && d512 >= 1) {
+            int64_t e_fit = 0, e_all = 0;
+            for (int k = p->k_lo; k < p->k_hi; k++) {
+                const int d = p->fptr[k + 1] - p->fptr[k];
+                e_all += d;
+                if (d <= d512) e_fit += d;
+            }
+            if (e_fit * 10 >= e_all * 9) tile_degree = d512;
+        }
+    }
+    if (tile_config2(p->HW, std::max(tile_degree, 1), false, p->NT)) {
         p->packed = true;
         p->PPT = 2;
-        if (p->dmax > kHubDegree) {
+        if (p->dmax > tile_degree) {
             for (int k = p->k_lo; k < p->k_hi; k++) {
                 const int d = p->fptr[k + 1] - p->fptr[k];
                 if (lin2_staging_bytes(d, p->NT) > lin2_staging_cap()) {
@@ -489,12 +506,7 @@ static int plan_create_impl(const int64_t *ii, const int64_t *jj, int64_t n_edge
                     p->dmax_bulk = std::max(p->dmax_bulk, d);
                 }
             }
-            if (p->flist_hub.empty()) {
-                p->flist_bulk.clear();  // everything fits: one launch
-            } else if (p->NT > 64) {
-                delete p;
-                return fail("internal: hub frames need the 64- or 32-slot tile");
-            }
+            if (p->flist_hub.empty()) p->flist_bulk.clear();  // everything fits: one launch
         }
     } else if (!tile_config(p->HW, std::max(p->dmax, 1), false, p->NT, p->PPT)) {
         delete p;

@@ -387,8 +387,10 @@ static cudaError_t launch_lin2_t(const LinArgs &a, int nframes, int dmax, cudaSt
 
 cudaError_t launch_linearize2(const LinArgs &a, int nframes, int dmax, bool motion, int NT, cudaStream_t st, bool ug) {
     if (nframes <= 0) return cudaSuccess;
-    if (ug) {  // hub frames: u staged in global memory (the narrow tiles are the ones a plan with hub frames uses)
+    if (ug) {  // hub frames: u staged in global memory
         if (motion || !a.uglobal) return cudaErrorInvalidValue;
+        if (NT == 256) return launch_lin2_t<256, false, true>(a, nframes, dmax, st);
+        if (NT == 128) return launch_lin2_t<128, false, true>(a, nframes, dmax, st);
         if (NT == 64) return launch_lin2_t<64, false, true>(a, nframes, dmax, st);
         if (NT == 32) return launch_lin2_t<32, false, true>(a, nframes, dmax, st);
         return cudaErrorInvalidValue;

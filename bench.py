@@ -25,6 +25,12 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+# torchrun exports OMP_NUM_THREADS=1 to its workers, and the OpenMP runtime reads it when it is loaded (with torch): the reference
+# arm's host code (Schur assembly, the LLT stand-in) is OpenMP code and gets every core of the box, as when it is run directly --
+# so the variable is fixed BEFORE torch is imported (and the runtime is told again in run_reference)
+if "--impl" in sys.argv and sys.argv[sys.argv.index("--impl") + 1: sys.argv.index("--impl") + 2] == ["reference"]:
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
@@ -141,6 +147,7 @@ def run_reference(args, pr):
     # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference's host code (Schur assembly, the LLT stand-in) is
     # OpenMP code and is given every core of the box, as when it is run directly
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    torch.set_num_threads(os.cpu_count() or 1)  # omp_set_num_threads on the runtime that is already loaded
     from oracle import build_ref
 
     cfg = pr.cfg
